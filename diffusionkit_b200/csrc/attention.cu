@@ -1,0 +1,359 @@
+// K3 — attention forward softmax(scale * Q K^T) V for sm_100a: tcgen05 MMAs with S and O accumulators in TMEM,
+// TMA-fed 128B-swizzled Q/K/V tiles, online softmax on S read back with tcgen05.ld.
+// Replaces mx.fast.scaled_dot_product_attention (reference mlx/mmdit.py:562-563,643,687-688,736): no mask,
+// non-causal, joint [text|image] sequence, head dim 64 (SD3) or 128 (FLUX).
+//
+// One CTA = 128 query rows of one (batch, head).  192 threads:
+//   warp 0     TMA producer : Q once, then K_j / V_j tiles (128 keys) through 2-stage rings
+//   warp 1     MMA issuer   : S_j = Q K_j^T   (M128 x N128 x K=d, both operands K-major)      -> TMEM S[j&1]
+//                             O  += P_j V_j   (M128 x N=d x K128; P K-major from smem, V MN-major as loaded) -> TMEM O
+//                             issue order QK_0, QK_1, PV_0, QK_2, PV_1, ... so QK_{j+1} overlaps softmax_j
+//   warps 2-5  softmax      : thread = query row (TMEM lane).  tcgen05.ld S row, running max / sum in the log2 domain,
+//                             P written to smem in the swizzled K-major layout the MMA expects, O rescaled in TMEM
+//                             only when the running max grew by more than 2^8 (lazy rescale), final O / l -> global.
+#include "common.cuh"
+#include "host.h"
+
+namespace dk {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 128;
+constexpr int ATT_THREADS = 192;
+
+template <int D>
+struct AttCfg {
+  static constexpr int TILE_BYTES = 128 * D * 2;     // Q / K / V tile
+  static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;
+  static constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = 512;  // S0 [0,128) S1 [128,256) O [256, 256+D)
+  static constexpr int TMEM_O = 256;
+};
+
+struct AttParams {
+  int B, S, heads, split;
+  float scale_log2;  // scale * log2(e)
+  void* out0;
+  long long ld0;
+  void* out1;
+  long long ld1;
+};
+
+template <typename T, int D>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+  using H16 = Half16<T>;
+  using Cfg = AttCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sP = smem + Cfg::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2]
+  uint64_t* s_empty = bars + 11;  // [2]
+  uint64_t* p_full = bars + 13;   // [2]
+  uint64_t* p_empty = bars + 15;  // [2]  (also: "PV_j retired")
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int h = p.heads * D;
+  const int n_tiles = (p.S + ATT_BKV - 1) / ATT_BKV;
+  const int row_base = b * p.S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 128);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&p_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      mbar_arrive_expect_tx(q_full, Cfg::TILE_BYTES);
+#pragma unroll
+      for (int a = 0; a < D / 64; ++a)
+        tma_load_2d(sQ + a * 16384, &tmQKV, q_full, head * D + a * 64, row_base + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j & 1;
+        const uint32_t par = static_cast<uint32_t>(j >> 1) & 1u;
+        const int kv_row = row_base + j * ATT_BKV;
+        mbar_wait(&k_empty[st], par ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a)
+          tma_load_2d(sK + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &k_full[st], h + head * D + a * 64, kv_row);
+        mbar_wait(&v_empty[st], par ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a)
+          tma_load_2d(sV + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &v_full[st], 2 * h + head * D + a * 64, kv_row);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_f16(ATT_BQ, ATT_BKV, H16::is_bf16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(ATT_BQ, D, H16::is_bf16, false, true);
+      const uint32_t q_addr = smem_u32(sQ);
+      auto issue_qk = [&](int i) {
+        const int st = i & 1;
+        const uint32_t par = static_cast<uint32_t>(i >> 1) & 1u;
+        mbar_wait(&k_full[st], par);
+        mbar_wait(&s_empty[st], par ^ 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + st * Cfg::TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + st * ATT_BKV;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 0, 1024), make_smem_desc_sw128(k_addr + off, 0, 1024),
+                  idesc_qk, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[st]);
+        umma_commit(&k_empty[st]);
+      };
+      auto issue_pv = [&](int i) {
+        const int st = i & 1;
+        const uint32_t par = static_cast<uint32_t>(i >> 1) & 1u;
+        mbar_wait(&v_full[st], par);
+        mbar_wait(&p_full[st], par);
+        tc_fence_after();
+        const uint32_t p_addr = smem_u32(sP + st * Cfg::P_BYTES);
+        const uint32_t v_addr = smem_u32(sV + st * Cfg::TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + Cfg::TMEM_O;
+#pragma unroll
+        for (int k = 0; k < ATT_BKV / 16; ++k) {
+          const uint32_t a_off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc_sw128(p_addr + a_off, 0, 1024),
+                  make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv, (i != 0 || k != 0) ? 1u : 0u);
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(&p_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);
+        issue_pv(j);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax / correction / epilogue
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // query row in the tile == TMEM lane
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    float m_run = -INFINITY;  // running max (log2 domain) that P and l are expressed against
+    float l_run = 0.f;
+    const float sl2 = p.scale_log2;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int st = j & 1;
+      const uint32_t par = static_cast<uint32_t>(j >> 1) & 1u;
+      mbar_wait(&s_full[st], par);
+      tc_fence_after();
+      uint32_t sr[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_lane + st * ATT_BKV + c * 32, sr[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&s_empty[st]);  // S[st] may be overwritten by QK_{j+2}
+
+      // scores in the log2 domain; keys beyond the sequence end (tail tile, or rows of the next batch / TMA zero fill)
+      // are masked out
+      const int kv_valid = p.S - j * ATT_BKV;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(sr[c][i]) * sl2;
+          if (c * 32 + i >= kv_valid) v = -INFINITY;
+          sr[c][i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      }
+      // lazy rescale: keep the stale max while the new one is within 2^8 of it (P stays <= 256, fine for fp32 sums
+      // and 16-bit P); decision is warp-uniform because the TMEM ld/st below are warp-collective
+      const float m_new = fmaxf(m_run, mx);
+      const bool need = (m_new - m_run) > 8.0f;  // also true on the first tile (m_run = -inf)
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = exp2f(m_run - m_new);  // 0 on the first tile
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+          // O must hold PV_{j-1} before it is rescaled
+          mbar_wait(&p_empty[(j - 1) & 1], static_cast<uint32_t>((j - 1) >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_lane + Cfg::TMEM_O + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_lane + Cfg::TMEM_O + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P = exp2(s - m_run) -> 16-bit, into smem in the K-major 128B-swizzled layout (two 64-key atoms of 128 rows)
+      mbar_wait(&p_empty[st], par ^ 1);  // PV_{j-2} has finished reading P[st]
+      uint8_t* p_row = sP + st * Cfg::P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // 8 keys per 16-byte chunk
+          float e[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e[i] = exp2f(__uint_as_float(sr[c][g * 8 + i]) - m_run);
+            lsum += e[i];
+          }
+          uint4 pk;
+          pk.x = H16::pack(e[0], e[1]);
+          pk.y = H16::pack(e[2], e[3]);
+          pk.z = H16::pack(e[4], e[5]);
+          pk.w = H16::pack(e[6], e[7]);
+          const int key = c * 32 + g * 8;
+          const int atom = key >> 6;
+          const int chunk = (key & 63) >> 3;
+          *reinterpret_cast<uint4*>(p_row + atom * 16384 + ((chunk ^ (r & 7)) << 4)) = pk;
+        }
+      }
+      l_run += lsum;
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      mbar_arrive(&p_full[st]);
+    }
+
+    // epilogue: O / l -> global.  PV_{n-1} retired <=> p_empty[(n-1)&1] completed its phase.
+    mbar_wait(&p_empty[(n_tiles - 1) & 1], static_cast<uint32_t>((n_tiles - 1) >> 1) & 1u);
+    tc_fence_after();
+    const int s_idx = q0 + r;
+    const bool row_ok = s_idx < p.S;
+    T* dst = nullptr;
+    if (row_ok) {
+      if (s_idx < p.split)
+        dst = reinterpret_cast<T*>(p.out0) + (static_cast<long long>(b) * p.split + s_idx) * p.ld0 + head * D;
+      else
+        dst = reinterpret_cast<T*>(p.out1) +
+              (static_cast<long long>(b) * (p.S - p.split) + (s_idx - p.split)) * p.ld1 + head * D;
+    }
+    const float inv_l = 1.0f / l_run;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + Cfg::TMEM_O + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = H16::pack(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          pk.y = H16::pack(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          pk.z = H16::pack(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          pk.w = H16::pack(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <typename T, int D>
+static int launch_attention(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+  using Cfg = AttCfg<D>;
+  auto kern = attention_fwd_kernel<T, D>;
+  static bool configured = false;
+  if (!configured) {
+    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(dk_ceil_div(p.S, ATT_BQ), p.heads, p.B);
+  kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, p);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace dk
+
+using namespace dk;
+
+extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, int S, int heads, int d, float scale,
+                                int split, void* out0, long long ld0, void* out1, long long ld1, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_attention_fwd: null ctx");
+  DK_REQUIRE(dtype == DK_BF16 || dtype == DK_FP16, "dk_attention_fwd: bad dtype %d", dtype);
+  DK_REQUIRE(d == 64 || d == 128, "dk_attention_fwd: head dim %d unsupported (64 or 128)", d);
+  DK_REQUIRE(B > 0 && S > 0 && heads > 0, "dk_attention_fwd: empty problem");
+  DK_REQUIRE(split >= 0 && split <= S, "dk_attention_fwd: split %d outside [0, %d]", split, S);
+  DK_REQUIRE(out0 != nullptr || split == 0, "dk_attention_fwd: out0 is NULL");
+  DK_REQUIRE(out1 != nullptr || split == S, "dk_attention_fwd: out1 is NULL but split < S");
+  DK_REQUIRE(ld0 % 8 == 0 && ld1 % 8 == 0, "dk_attention_fwd: output leading dims must be multiples of 8");
+  DK_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out0) & 15u) == 0 &&
+                 (reinterpret_cast<uintptr_t>(out1) & 15u) == 0,
+             "dk_attention_fwd: buffers must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int h = heads * d;
+  CUtensorMap tm;
+  const uint64_t dims[2] = {static_cast<uint64_t>(3 * h), static_cast<uint64_t>(B) * S};
+  const uint64_t strides[1] = {static_cast<uint64_t>(3 * h) * 2};
+  const uint32_t box[2] = {64, 128};
+  if (int rc = dk_make_tmap_16b(ctx, &tm, qkv, 2, dims, strides, box)) return rc;
+  AttParams p;
+  p.B = B;
+  p.S = S;
+  p.heads = heads;
+  p.split = split;
+  p.scale_log2 = scale * 1.44269504088896341f;
+  p.out0 = out0;
+  p.ld0 = ld0;
+  p.out1 = out1;
+  p.ld1 = ld1;
+  if (dtype == DK_BF16) {
+    if (d == 128) return launch_attention<__nv_bfloat16, 128>(ctx, tm, p, stream);
+    return launch_attention<__nv_bfloat16, 64>(ctx, tm, p, stream);
+  }
+  if (d == 128) return launch_attention<__half, 128>(ctx, tm, p, stream);
+  return launch_attention<__half, 64>(ctx, tm, p, stream);
+}

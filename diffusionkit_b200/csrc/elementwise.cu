@@ -1,0 +1,768 @@
+// HBM-bound kernels of the denoise + decode path: normalisations, modulation, RoPE, layout shuffles, sampler update.
+// All of them move 128-bit vectors per thread, reduce with warp shuffles, and do their arithmetic in fp32.
+#include "common.cuh"
+#include "host.h"
+
+namespace dk {
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = Half16<T>::unpack(w[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&v)[8]) {
+  uint4 o;
+  o.x = Half16<T>::pack(v[0], v[1]);
+  o.y = Half16<T>::pack(v[2], v[3]);
+  o.z = Half16<T>::pack(v[4], v[5]);
+  o.w = Half16<T>::pack(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+template <typename T>
+__device__ __forceinline__ float round16(float v) {
+  return Half16<T>::to_f(Half16<T>::from_f(v));
+}
+
+// block-wide sum for blockDim.x = NT (multiple of 32); every thread gets the result
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < NT / 32) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+template <int NT>
+__device__ __forceinline__ float block_max(float v, float* red) {
+  v = warp_max(v);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < NT / 32) ? red[lane] : -INFINITY;
+  t = warp_max(t);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: LayerNorm (no affine) + adaLN modulate.  One 128-thread block per row, row kept in registers.
+//     mlx.fast.layer_norm semantics: biased variance, fp32 accumulation, (x-mu)*rsqrt(var+eps)*w + b with
+//     w = 1 + scale, b = shift (reference mlx/mmdit.py:958-972).
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_THREADS = 128;
+constexpr int LN_MAXV = 4;  // h <= 128 * 8 * 4 = 4096
+
+template <typename T>
+__global__ void __launch_bounds__(LN_THREADS)
+ln_modulate_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ shift, const T* __restrict__ scale,
+                   long long mod_ld, int rows_per_batch, int h, float eps) {
+  __shared__ float red[LN_THREADS / 32];
+  const int row = blockIdx.x;
+  const int b = row / rows_per_batch;
+  const T* xr = x + static_cast<long long>(row) * h;
+  T* yr = y + static_cast<long long>(row) * h;
+  const int nvec = h / 8;
+  float v[LN_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vec = threadIdx.x + i * LN_THREADS;
+    if (vec < nvec) {
+      load8(xr + vec * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = block_sum<LN_THREADS>(s, red) / h;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vec = threadIdx.x + i * LN_THREADS;
+    if (vec < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum<LN_THREADS>(q, red) / h + eps);
+  const T* sh = shift + static_cast<long long>(b) * mod_ld;
+  const T* sc = scale + static_cast<long long>(b) * mod_ld;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vec = threadIdx.x + i * LN_THREADS;
+    if (vec < nvec) {
+      float a[8], c[8], o[8];
+      load8(sc + vec * 8, a);
+      load8(sh + vec * 8, c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * (1.0f + a[j]) + c[j];
+      store8(yr + vec * 8, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// QK-RMSNorm + RoPE, in place on the q and k thirds of the packed QKV buffer.  One warp per (row, head, q|k).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int D>
+__global__ void __launch_bounds__(256)
+qk_norm_rope_kernel(T* __restrict__ qkv, int rows, int S, int heads, int split, const T* __restrict__ q_w,
+                    const T* __restrict__ k_w, const T* __restrict__ q_w2, const T* __restrict__ k_w2,
+                    const float* __restrict__ rope, float eps) {
+  constexpr int EPL = D / 32;  // elements per lane: 2 (d=64) or 4 (d=128)
+  const long long gw = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(rows) * heads * 2;
+  if (gw >= total) return;
+  const int which = static_cast<int>(gw % 2);  // 0 = q, 1 = k
+  const int head = static_cast<int>((gw / 2) % heads);
+  const long long row = gw / (2LL * heads);
+  const int pos = static_cast<int>(row % S);
+  const int h = heads * D;
+  T* p = qkv + row * (3LL * h) + static_cast<long long>(which) * h + head * D + lane * EPL;
+
+  float v[EPL];
+  if (EPL == 4) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = Half16<T>::unpack(u.x), b = Half16<T>::unpack(u.y);
+    v[0] = a.x;
+    v[1] = a.y;
+    v[EPL - 2] = b.x;
+    v[EPL - 1] = b.y;
+  } else {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+    const float2 a = Half16<T>::unpack(u);
+    v[0] = a.x;
+    v[1] = a.y;
+  }
+  const T* w = (pos < split) ? (which == 0 ? q_w : k_w) : (which == 0 ? q_w2 : k_w2);
+  if (w != nullptr) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) ss += v[i] * v[i];
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / D + eps);
+#pragma unroll
+    for (int i = 0; i < EPL; ++i)
+      v[i] = round16<T>(v[i] * rstd * Half16<T>::to_f(w[lane * EPL + i]));  // nn.RMSNorm output in the activation dtype
+  }
+  if (rope != nullptr) {
+    // rope[pos][pair] = (cos, sin); out = (x0 cos - x1 sin, x0 sin + x1 cos)  — mlx/mmdit.py:934-942
+    const float* rp = rope + (static_cast<long long>(pos) * (D / 2) + lane * (EPL / 2)) * 2;
+#pragma unroll
+    for (int i = 0; i < EPL / 2; ++i) {
+      const float c = rp[2 * i], sn = rp[2 * i + 1];
+      const float x0 = v[2 * i], x1 = v[2 * i + 1];
+      v[2 * i] = x0 * c - x1 * sn;
+      v[2 * i + 1] = x0 * sn + x1 * c;
+    }
+  }
+  if (EPL == 4) {
+    uint2 o;
+    o.x = Half16<T>::pack(v[0], v[1]);
+    o.y = Half16<T>::pack(v[EPL - 2], v[EPL - 1]);
+    *reinterpret_cast<uint2*>(p) = o;
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = Half16<T>::pack(v[0], v[1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise kernels (grid-stride over 8-element vectors)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void silu_add_kernel(const T* __restrict__ y, const T* __restrict__ temb, T* __restrict__ c, int n_t, int B,
+                                int h) {
+  const long long nvec = static_cast<long long>(n_t) * B * h / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int col = static_cast<int>(e % h);
+    const long long row = e / h;
+    const int b = static_cast<int>(row % B);
+    const int t = static_cast<int>(row / B);
+    float a[8], d[8], o[8];
+    load8(y + static_cast<long long>(b) * h + col, a);
+    load8(temb + static_cast<long long>(t) * h + col, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = silu_f(round16<T>(a[j] + d[j]));
+    store8(c + e, o);
+  }
+}
+
+template <typename T>
+__global__ void act_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act) {
+  const long long nvec = n / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float a[8];
+    load8(x + i * 8, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = act == DK_ACT_SILU ? silu_f(a[j]) : (act == DK_ACT_GELU_ERF ? gelu_erf(a[j]) : a[j]);
+    store8(y + i * 8, a);
+  }
+}
+
+// patchify / unpatchify: one thread per (token, output feature)
+template <typename T>
+__global__ void patchify_kernel(const T* __restrict__ latent, T* __restrict__ rows, int B, int H, int W, int C,
+                                int order) {
+  const int F = 4 * C;
+  const long long total = static_cast<long long>(B) * (H / 2) * (W / 2) * F;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int f = static_cast<int>(i % F);
+    const long long tok = i / F;
+    const int wp = static_cast<int>(tok % (W / 2));
+    const int hp = static_cast<int>((tok / (W / 2)) % (H / 2));
+    const int b = static_cast<int>(tok / (static_cast<long long>(W / 2) * (H / 2)));
+    int c, ph, pw;
+    if (order == 0) {  // (c, ph, pw)
+      c = f / 4;
+      ph = (f / 2) % 2;
+      pw = f % 2;
+    } else {  // (ph, pw, c)
+      ph = f / (2 * C);
+      pw = (f / C) % 2;
+      c = f % C;
+    }
+    rows[i] = latent[((static_cast<long long>(b) * H + 2 * hp + ph) * W + 2 * wp + pw) * C + c];
+  }
+}
+template <typename T>
+__global__ void unpatchify_kernel(const T* __restrict__ rows, T* __restrict__ latent, int B, int H, int W, int C,
+                                  int order) {
+  const int F = 4 * C;
+  const long long total = static_cast<long long>(B) * H * W * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int x = static_cast<int>((i / C) % W);
+    const int y = static_cast<int>((i / (static_cast<long long>(C) * W)) % H);
+    const int b = static_cast<int>(i / (static_cast<long long>(C) * W * H));
+    const int ph = y & 1, pw = x & 1;
+    const long long tok = (static_cast<long long>(b) * (H / 2) + y / 2) * (W / 2) + x / 2;
+    const int f = order == 0 ? (c * 4 + ph * 2 + pw) : ((ph * 2 + pw) * C + c);
+    latent[i] = rows[tok * F + f];
+  }
+}
+
+template <typename T>
+__global__ void pos_embed_crop_kernel(const T* __restrict__ table, T* __restrict__ out, int max_hw, int hp, int wp,
+                                      int h) {
+  const int y0 = (max_hw - hp) / 2, x0 = (max_hw - wp) / 2;
+  const long long nvec = static_cast<long long>(hp) * wp * h / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int col = static_cast<int>(e % h);
+    const long long tok = e / h;
+    const int xx = static_cast<int>(tok % wp), yy = static_cast<int>(tok / wp);
+    *reinterpret_cast<uint4*>(out + e) =
+        *reinterpret_cast<const uint4*>(table + (static_cast<long long>(y0 + yy) * max_hw + x0 + xx) * h + col);
+  }
+}
+
+template <typename T>
+__global__ void copy_rows_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int rows, int h, int dst_rows,
+                                 int dst_off, int src_rows, int src_off) {
+  const long long nvec = static_cast<long long>(B) * rows * h / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int col = static_cast<int>(e % h);
+    const long long rr = e / h;
+    const int r = static_cast<int>(rr % rows);
+    const int b = static_cast<int>(rr / rows);
+    *reinterpret_cast<uint4*>(dst + (static_cast<long long>(b) * dst_rows + dst_off + r) * h + col) =
+        *reinterpret_cast<const uint4*>(src + (static_cast<long long>(b) * src_rows + src_off + r) * h + col);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler (fp32 state) — reference mlx/__init__.py:691-719, 775-782; mlx/sampler.py:37-39
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sampler_prepare_kernel(const float* __restrict__ x, T* __restrict__ xin, long long n, int reps) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const T v = Half16<T>::from_f(x[i]);
+    for (int k = 0; k < reps; ++k) xin[k * n + i] = v;
+  }
+}
+template <typename T>
+__global__ void sampler_step_kernel(float* __restrict__ x, const T* __restrict__ xin, const T* __restrict__ out,
+                                    long long n, float sigma, float sigma_next, float cfg) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // calculate_denoised: model_input - model_output * sigma (fp32 sigma promotes to fp32)
+    float den = Half16<T>::to_f(xin[i]) - Half16<T>::to_f(out[i]) * sigma;
+    if (cfg > 0.f) {
+      const float den_neg = Half16<T>::to_f(xin[n + i]) - Half16<T>::to_f(out[n + i]) * sigma;
+      den = den_neg + cfg * (den - den_neg);
+    }
+    const float xv = x[i];
+    const float d = (xv - den) / sigma;          // to_d
+    x[i] = xv + d * (sigma_next - sigma);        // Euler
+  }
+}
+__global__ void axpb_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float a, float b) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = x[i] * a + b;
+}
+template <typename T>
+__global__ void cast_f32_to_16_kernel(const float* __restrict__ x, T* __restrict__ y, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = Half16<T>::from_f(x[i]);
+}
+template <typename T>
+__global__ void cast_16_to_f32_kernel(const T* __restrict__ x, float* __restrict__ y, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] = Half16<T>::to_f(x[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm (VAE).  stats: two-stage, deterministic (no atomics):
+//   stage 1: grid (GN_CHUNKS, B); each block reduces its pixel slab to per-group (sum, sumsq) partials
+//   stage 2: one warp per (b, g) folds the partials in double and writes (mean, rstd)
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_CHUNKS = 64;
+constexpr int GN_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C, int G) {
+  extern __shared__ float sm[];  // [2*C]
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int per = (HW + GN_CHUNKS - 1) / GN_CHUNKS;
+  const int p0 = chunk * per;
+  const int p1 = min(HW, p0 + per);
+  const int vec_per_pix = C / 8;
+  const int pix_per_iter = GN_THREADS / vec_per_pix;  // C <= 2048
+  const int my_vec = threadIdx.x % vec_per_pix;
+  const int my_pix = threadIdx.x / vec_per_pix;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (my_pix < pix_per_iter) {
+    for (int p = p0 + my_pix; p < p1; p += pix_per_iter) {
+      float v[8];
+      load8(x + (static_cast<long long>(b) * HW + p) * C + my_vec * 8, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v[j];
+        q[j] += v[j] * v[j];
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+  __syncthreads();
+  if (my_pix < pix_per_iter) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[my_vec * 8 + j], s[j]);
+      atomicAdd(&sm[C + my_vec * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += GN_THREADS) {
+    float ts = 0.f, tq = 0.f;
+    for (int c = 0; c < cpg; ++c) {
+      ts += sm[g * cpg + c];
+      tq += sm[C + g * cpg + c];
+    }
+    float* dst = partial + ((static_cast<long long>(b) * GN_CHUNKS + chunk) * G + g) * 2;
+    dst[0] = ts;
+    dst[1] = tq;
+  }
+}
+__global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int B, int G,
+                                          double count, float eps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * G) return;
+  const int b = idx / G, g = idx % G;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < GN_CHUNKS; ++c) {
+    const float* p = partial + ((static_cast<long long>(b) * GN_CHUNKS + c) * G + g) * 2;
+    s += p[0];
+    q += p[1];
+  }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[idx * 2] = static_cast<float>(mean);
+  stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+}
+template <typename T>
+__global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
+                                       const T* __restrict__ gamma, const T* __restrict__ beta, int B, int HW, int C,
+                                       int G, int silu) {
+  const long long nvec = static_cast<long long>(B) * HW * C / 8;
+  const int cpg = C / G;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 8;
+    const int c0 = static_cast<int>(e % C);
+    const int b = static_cast<int>(e / (static_cast<long long>(HW) * C));
+    float v[8], ga[8], be[8];
+    load8(x + e, v);
+    load8(gamma + c0, ga);
+    load8(beta + c0, be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c0 + j) / cpg;
+      const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
+      float o = (v[j] - mean) * rstd * ga[j] + be[j];
+      if (silu) o = silu_f(round16<T>(o));
+      v[j] = o;
+    }
+    store8(y + e, v);
+  }
+}
+
+template <typename T>
+__global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  // y: [B, 2H, 2W, C]
+  const long long nvec = static_cast<long long>(B) * 4 * H * W * C / 8;
+  const int vpp = C / 8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(i % vpp);
+    const long long pix = i / vpp;
+    const int ox = static_cast<int>(pix % (2 * W));
+    const int oy = static_cast<int>((pix / (2 * W)) % (2 * H));
+    const int b = static_cast<int>(pix / (4LL * W * H));
+    *reinterpret_cast<uint4*>(y + pix * C + v * 8) =
+        *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * H + oy / 2) * W + ox / 2) * C + v * 8);
+  }
+}
+
+// row softmax (VAE mid-block attention, reference mlx/vae.py:49-52): p = softmax(scale * s), fp32 math, 16-bit out
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(T* __restrict__ x, int n, long long ld, float scale) {
+  __shared__ float red[8];
+  T* row = x + static_cast<long long>(blockIdx.x) * ld;
+  const int nvec = n / 8;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    float v[8];
+    load8(row + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, v[j]);
+  }
+  mx = block_max<256>(mx, red);
+  const float k = scale * 1.44269504088896341f;
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    float v[8];
+    load8(row + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += exp2f((v[j] - mx) * k);
+  }
+  sum = block_sum<256>(sum, red);
+  const float inv = 1.0f / sum;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    float v[8];
+    load8(row + i * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = exp2f((v[j] - mx) * k) * inv;
+    store8(row + i * 8, v);
+  }
+}
+
+// decode tail: clip(x/2 + 0.5, 0, 1) in the activation dtype (mlx/__init__.py:583), uint8 = trunc(x * 255) (:526)
+template <typename T>
+__global__ void image_post_kernel(const T* __restrict__ x, int c_stride, float* __restrict__ img_f32,
+                                  uint8_t* __restrict__ img_u8, long long pixels) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < pixels * 3;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / 3;
+    const int c = static_cast<int>(i % 3);
+    float v = Half16<T>::to_f(x[p * c_stride + c]);
+    v = round16<T>(round16<T>(v * 0.5f) + 0.5f);
+    v = fminf(fmaxf(v, 0.f), 1.f);
+    if (img_f32 != nullptr) img_f32[i] = v;
+    if (img_u8 != nullptr) img_u8[i] = static_cast<uint8_t>(round16<T>(v * 255.f));
+  }
+}
+
+static inline int grid_for(long long work_items, int threads, int sm_count) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = static_cast<long long>(sm_count) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace dk
+
+using namespace dk;
+
+#define DK_DTYPE_OK(dt) DK_REQUIRE((dt) == DK_BF16 || (dt) == DK_FP16, "%s: bad dtype %d", __func__, (dt))
+#define DK_DISPATCH(dt, ...)                      \
+  do {                                            \
+    if ((dt) == DK_BF16) {                        \
+      using T = __nv_bfloat16;                    \
+      __VA_ARGS__;                                \
+    } else {                                      \
+      using T = __half;                           \
+      __VA_ARGS__;                                \
+    }                                             \
+  } while (0)
+
+extern "C" int dk_ln_modulate(dk_ctx* ctx, int dtype, const void* x, void* y, const void* shift, const void* scale,
+                              long long mod_ld, int rows, int rows_per_batch, int h, float eps, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_ln_modulate: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(rows > 0 && rows_per_batch > 0, "dk_ln_modulate: empty input");
+  DK_REQUIRE(h % 8 == 0 && h <= LN_THREADS * 8 * LN_MAXV, "dk_ln_modulate: h=%d unsupported (multiple of 8, <= %d)", h,
+             LN_THREADS * 8 * LN_MAXV);
+  DK_REQUIRE(mod_ld % 8 == 0, "dk_ln_modulate: mod_ld must be a multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (ln_modulate_kernel<T><<<rows, LN_THREADS, 0, stream>>>(
+                         static_cast<const T*>(x), static_cast<T*>(y), static_cast<const T*>(shift),
+                         static_cast<const T*>(scale), mod_ld, rows_per_batch, h, eps)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_qk_norm_rope(dk_ctx* ctx, int dtype, void* qkv, int rows, int S, int heads, int d, int split,
+                               const void* q_w, const void* k_w, const void* q_w2, const void* k_w2, const float* rope,
+                               float eps, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_qk_norm_rope: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(d == 64 || d == 128, "dk_qk_norm_rope: head dim %d unsupported (64 or 128)", d);
+  DK_REQUIRE(rows > 0 && S > 0 && rows % S == 0, "dk_qk_norm_rope: rows %d must be a multiple of S %d", rows, S);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long warps = static_cast<long long>(rows) * heads * 2;
+  const int blocks = static_cast<int>((warps * 32 + 255) / 256);
+  if (q_w2 == nullptr) q_w2 = q_w;
+  if (k_w2 == nullptr) k_w2 = k_w;
+  DK_DISPATCH(dtype, {
+    if (d == 128)
+      qk_norm_rope_kernel<T, 128><<<blocks, 256, 0, stream>>>(
+          static_cast<T*>(qkv), rows, S, heads, split, static_cast<const T*>(q_w), static_cast<const T*>(k_w),
+          static_cast<const T*>(q_w2), static_cast<const T*>(k_w2), rope, eps);
+    else
+      qk_norm_rope_kernel<T, 64><<<blocks, 256, 0, stream>>>(
+          static_cast<T*>(qkv), rows, S, heads, split, static_cast<const T*>(q_w), static_cast<const T*>(k_w),
+          static_cast<const T*>(q_w2), static_cast<const T*>(k_w2), rope, eps);
+  });
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_silu_add(dk_ctx* ctx, int dtype, const void* y, const void* temb, void* c, int n_t, int B, int h,
+                           void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_silu_add: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(h % 8 == 0, "dk_silu_add: h must be a multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long nvec = static_cast<long long>(n_t) * B * h / 8;
+  DK_DISPATCH(dtype, (silu_add_kernel<T><<<grid_for(nvec, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(y), static_cast<const T*>(temb), static_cast<T*>(c), n_t, B, h)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_act(dk_ctx* ctx, int dtype, const void* x, void* y, long long n, int act, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_act: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(n % 8 == 0, "dk_act: n must be a multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (act_kernel<T><<<grid_for(n / 8, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(x), static_cast<T*>(y), n, act)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_patchify(dk_ctx* ctx, int dtype, const void* latent, void* rows, int B, int H, int W, int C, int order,
+                           void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_patchify: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(H % 2 == 0 && W % 2 == 0, "dk_patchify: latent size must be even (got %dx%d)", H, W);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long total = static_cast<long long>(B) * H * W * C;
+  DK_DISPATCH(dtype, (patchify_kernel<T><<<grid_for(total, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(latent), static_cast<T*>(rows), B, H, W, C, order)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_unpatchify(dk_ctx* ctx, int dtype, const void* rows, void* latent, int B, int H, int W, int C,
+                             int order, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_unpatchify: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(H % 2 == 0 && W % 2 == 0, "dk_unpatchify: latent size must be even (got %dx%d)", H, W);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long total = static_cast<long long>(B) * H * W * C;
+  DK_DISPATCH(dtype, (unpatchify_kernel<T><<<grid_for(total, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(rows), static_cast<T*>(latent), B, H, W, C, order)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_pos_embed_crop(dk_ctx* ctx, int dtype, const void* table, void* out, int max_hw, int hp, int wp, int h,
+                                 void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_pos_embed_crop: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(hp <= max_hw && wp <= max_hw, "dk_pos_embed_crop: %dx%d exceeds the %d table", hp, wp, max_hw);
+  DK_REQUIRE(h % 8 == 0, "dk_pos_embed_crop: h must be a multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long nvec = static_cast<long long>(hp) * wp * h / 8;
+  DK_DISPATCH(dtype, (pos_embed_crop_kernel<T><<<grid_for(nvec, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(table), static_cast<T*>(out), max_hw, hp, wp, h)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_copy_rows(dk_ctx* ctx, int dtype, const void* src, void* dst, int B, int rows, int h, int dst_rows,
+                            int dst_off, int src_rows, int src_off, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_copy_rows: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(h % 8 == 0, "dk_copy_rows: h must be a multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long nvec = static_cast<long long>(B) * rows * h / 8;
+  DK_DISPATCH(dtype, (copy_rows_kernel<T><<<grid_for(nvec, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(src), static_cast<T*>(dst), B, rows, h, dst_rows, dst_off, src_rows,
+                         src_off)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_sampler_prepare(dk_ctx* ctx, int dtype, const float* x, void* xin, long long n_per_rep, int reps,
+                                  void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_sampler_prepare: null ctx");
+  DK_DTYPE_OK(dtype);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (sampler_prepare_kernel<T><<<grid_for(n_per_rep, 256, ctx->sm_count), 256, 0, stream>>>(
+                         x, static_cast<T*>(xin), n_per_rep, reps)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_sampler_step(dk_ctx* ctx, int dtype, float* x, const void* xin, const void* out, long long n,
+                               float sigma, float sigma_next, float cfg_weight, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_sampler_step: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(sigma != 0.f, "dk_sampler_step: sigma must be non-zero");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (sampler_step_kernel<T><<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(
+                         x, static_cast<const T*>(xin), static_cast<const T*>(out), n, sigma, sigma_next, cfg_weight)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, float a, float b, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_axpb_f32: null ctx");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  axpb_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(x, y, n, a, b);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_cast_f32_to_16(dk_ctx* ctx, int dtype, const float* x, void* y, long long n, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_cast_f32_to_16: null ctx");
+  DK_DTYPE_OK(dtype);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (cast_f32_to_16_kernel<T><<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(
+                         x, static_cast<T*>(y), n)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+extern "C" int dk_cast_16_to_f32(dk_ctx* ctx, int dtype, const void* x, float* y, long long n, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_cast_16_to_f32: null ctx");
+  DK_DTYPE_OK(dtype);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (cast_16_to_f32_kernel<T><<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(x), y, n)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_groupnorm_ws_floats(int B, int G) { return B * GN_CHUNKS * G * 2; }
+
+extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* stats, float* ws, int B, int HW, int C,
+                                  int G, float eps, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_groupnorm_stats: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 2048, "dk_groupnorm_stats: C=%d G=%d unsupported", C, G);
+  DK_REQUIRE(ws != nullptr, "dk_groupnorm_stats: workspace of dk_groupnorm_ws_floats(B, G) floats required");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  dim3 grid(GN_CHUNKS, B);
+  DK_DISPATCH(dtype, (groupnorm_partial_kernel<T><<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(
+                         static_cast<const T*>(x), ws, HW, C, G)));
+  DK_LAUNCH_CHECK(ctx);
+  groupnorm_finalize_kernel<<<(B * G + 127) / 128, 128, 0, stream>>>(
+      ws, stats, B, G, static_cast<double>(HW) * (C / G), eps);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_groupnorm_apply(dk_ctx* ctx, int dtype, const void* x, void* y, const float* stats, const void* gamma,
+                                  const void* beta, int B, int HW, int C, int G, int silu, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_groupnorm_apply: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(C % 8 == 0 && C % G == 0, "dk_groupnorm_apply: C=%d G=%d unsupported", C, G);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long nvec = static_cast<long long>(B) * HW * C / 8;
+  DK_DISPATCH(dtype, (groupnorm_apply_kernel<T><<<grid_for(nvec, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(x), static_cast<T*>(y), stats, static_cast<const T*>(gamma),
+                         static_cast<const T*>(beta), B, HW, C, G, silu)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_upsample_nearest2x(dk_ctx* ctx, int dtype, const void* x, void* y, int B, int H, int W, int C,
+                                     void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_upsample_nearest2x: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(C % 8 == 0, "dk_upsample_nearest2x: C must be a multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long nvec = static_cast<long long>(B) * 4 * H * W * C / 8;
+  DK_DISPATCH(dtype, (upsample2x_kernel<T><<<grid_for(nvec, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(x), static_cast<T*>(y), B, H, W, C)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_softmax_rows(dk_ctx* ctx, int dtype, void* x, long long rows, int n, long long ld, float scale,
+                               void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_softmax_rows: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(n % 8 == 0 && ld % 8 == 0, "dk_softmax_rows: n and ld must be multiples of 8");
+  DK_REQUIRE(rows > 0 && rows < (1LL << 31), "dk_softmax_rows: bad row count");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (softmax_rows_kernel<T><<<static_cast<unsigned>(rows), 256, 0, stream>>>(static_cast<T*>(x), n, ld,
+                                                                                             scale)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_image_post(dk_ctx* ctx, int dtype, const void* x, int c_stride, float* img_f32, uint8_t* img_u8,
+                             long long pixels, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_image_post: null ctx");
+  DK_DTYPE_OK(dtype);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (image_post_kernel<T><<<grid_for(pixels * 3, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(x), c_stride, img_f32, img_u8, pixels)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}

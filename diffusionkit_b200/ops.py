@@ -1,0 +1,304 @@
+"""Typed Python wrappers over the C ABI (torch tensors are only the device-memory containers).
+
+Every function launches hand-written sm_100a kernels from libdkb200.so asynchronously on the current
+torch CUDA stream.  Nothing here has a torch / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_SILU, Context, GemmArgs, dtype_code, ptr
+
+_ctx = {}
+
+
+def ctx(device: Optional[int] = None) -> Context:
+    if device is None:
+        device = torch.cuda.current_device()
+    c = _ctx.get(device)
+    if c is None:
+        c = Context(device)
+        _ctx[device] = c
+    return c
+
+
+def launch_count() -> int:
+    return sum(c.launches for c in _ctx.values())
+
+
+def _chk16(t: torch.Tensor, name: str):
+    if t.dtype not in (torch.bfloat16, torch.float16):
+        raise _lib.DkError(f"{name}: expected a bf16/fp16 tensor, got {t.dtype}")
+    if not t.is_cuda:
+        raise _lib.DkError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
+
+
+def gemm(
+    A: torch.Tensor,
+    W: torch.Tensor,
+    out: Optional[torch.Tensor] = None,
+    bias: Optional[torch.Tensor] = None,
+    act: int = ACT_NONE,
+    gate: Optional[torch.Tensor] = None,
+    res: Optional[torch.Tensor] = None,
+    rows_per_batch: int = 0,
+    out_batch_rows: int = 0,
+    out_row_off: int = 0,
+    res_batch_rows: Optional[int] = None,
+    res_row_off: int = 0,
+    w_n_major: bool = False,
+    N: Optional[int] = None,
+) -> torch.Tensor:
+    """out = res + gate * act(A @ W.T + bias)   (see include/dkb200.h, dk_gemm).
+
+    A: [M, K] (row stride may exceed K), W: [N, K] (nn.Linear layout) or [K, N] when w_n_major.
+    out: 2-D view [rows, >=N] whose row stride is the leading dimension.
+    """
+    _chk16(A, "gemm.A")
+    _chk16(W, "gemm.W")
+    assert A.dim() == 2 and W.dim() == 2 and A.stride(1) == 1 and W.stride(1) == 1
+    M, K = A.shape
+    if w_n_major:
+        assert W.shape[0] == K
+        n = W.shape[1]
+    else:
+        assert W.shape[1] == K, f"K mismatch {A.shape} x {W.shape}"
+        n = W.shape[0]
+    if N is not None:
+        n = N
+    if out is None:
+        out = torch.empty((M, n), dtype=A.dtype, device=A.device)
+    assert out.dim() == 2 and out.stride(1) == 1
+    a = GemmArgs()
+    a.dtype = dtype_code(A.dtype)
+    a.M, a.N, a.K = M, n, K
+    a.A, a.lda = ptr(A), A.stride(0)
+    a.W, a.ldw = ptr(W), W.stride(0)
+    a.out, a.ldc = ptr(out), out.stride(0)
+    a.bias = ptr(bias)
+    a.gate = ptr(gate)
+    a.gate_ld = gate.stride(0) if gate is not None else 0
+    a.res = ptr(res)
+    a.ldres = res.stride(0) if res is not None else 0
+    a.rows_per_batch = rows_per_batch
+    a.out_batch_rows = out_batch_rows if rows_per_batch else 0
+    a.out_row_off = out_row_off
+    if res_batch_rows is None:
+        res_batch_rows = rows_per_batch
+    a.res_batch_rows = res_batch_rows if rows_per_batch else 0
+    a.res_row_off = res_row_off
+    a.act = act
+    a.w_n_major = 1 if w_n_major else 0
+    c = ctx(A.device.index)
+    c.check(c.lib.dk_gemm(c.handle, C.byref(a), c.stream))
+    return out
+
+
+def ln_modulate(x, shift, scale, rows_per_batch: int, eps: float = 1e-6, out=None):
+    """y = LN(x) * (1 + scale[b]) + shift[b]; x [rows, h]; shift/scale 2-D views [B, h] (row stride = mod_ld)."""
+    _chk16(x, "ln_modulate.x")
+    rows, h = x.shape
+    assert x.is_contiguous() and shift.stride(0) == scale.stride(0) and shift.stride(1) == 1
+    if out is None:
+        out = torch.empty_like(x)
+    c = ctx(x.device.index)
+    c.call("dk_ln_modulate", dtype_code(x.dtype), ptr(x), ptr(out), ptr(shift), ptr(scale), shift.stride(0), rows,
+           rows_per_batch, h, eps)
+    return out
+
+
+def qk_norm_rope(qkv, S: int, heads: int, d: int, split: int, q_w=None, k_w=None, q_w2=None, k_w2=None, rope=None,
+                 eps: float = 1e-6):
+    _chk16(qkv, "qk_norm_rope.qkv")
+    assert qkv.is_contiguous() and qkv.shape[1] == 3 * heads * d
+    if rope is not None:
+        assert rope.dtype == torch.float32 and rope.is_contiguous() and rope.numel() == S * d
+    c = ctx(qkv.device.index)
+    c.call("dk_qk_norm_rope", dtype_code(qkv.dtype), ptr(qkv), qkv.shape[0], S, heads, d, split, ptr(q_w), ptr(k_w),
+           ptr(q_w2), ptr(k_w2), ptr(rope), eps)
+    return qkv
+
+
+def attention(qkv, B: int, S: int, heads: int, d: int, out0, split: Optional[int] = None, out1=None,
+              scale: Optional[float] = None):
+    """softmax(scale q k^T) v over the packed [B*S, 3*heads*d] buffer; rows < split go to out0, the rest to out1."""
+    _chk16(qkv, "attention.qkv")
+    assert qkv.is_contiguous() and qkv.shape == (B * S, 3 * heads * d)
+    if split is None:
+        split = S
+    if scale is None:
+        scale = 1.0 / math.sqrt(d)
+    c = ctx(qkv.device.index)
+    c.call("dk_attention_fwd", dtype_code(qkv.dtype), ptr(qkv), B, S, heads, d, scale, split, ptr(out0),
+           out0.stride(0) if out0 is not None else 0, ptr(out1), out1.stride(0) if out1 is not None else 0)
+    return out0, out1
+
+
+def silu_add(y, temb, out=None):
+    """out[t*B + b] = silu(y[b] + temb[t])."""
+    _chk16(y, "silu_add.y")
+    B, h = y.shape
+    n_t = temb.shape[0]
+    if out is None:
+        out = torch.empty((n_t * B, h), dtype=y.dtype, device=y.device)
+    c = ctx(y.device.index)
+    c.call("dk_silu_add", dtype_code(y.dtype), ptr(y), ptr(temb), ptr(out), n_t, B, h)
+    return out
+
+
+def act(x, kind: int, out=None):
+    _chk16(x, "act.x")
+    if out is None:
+        out = torch.empty_like(x)
+    c = ctx(x.device.index)
+    c.call("dk_act", dtype_code(x.dtype), ptr(x), ptr(out), x.numel(), kind)
+    return out
+
+
+def patchify(latent, order: int, out=None):
+    _chk16(latent, "patchify.latent")
+    B, H, W, Cc = latent.shape
+    if out is None:
+        out = torch.empty((B * (H // 2) * (W // 2), 4 * Cc), dtype=latent.dtype, device=latent.device)
+    c = ctx(latent.device.index)
+    c.call("dk_patchify", dtype_code(latent.dtype), ptr(latent), ptr(out), B, H, W, Cc, order)
+    return out
+
+
+def unpatchify(rows, B: int, H: int, W: int, Cc: int, order: int, out=None):
+    _chk16(rows, "unpatchify.rows")
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=rows.dtype, device=rows.device)
+    c = ctx(rows.device.index)
+    c.call("dk_unpatchify", dtype_code(rows.dtype), ptr(rows), ptr(out), B, H, W, Cc, order)
+    return out
+
+
+def pos_embed_crop(table, max_hw: int, hp: int, wp: int):
+    _chk16(table, "pos_embed_crop.table")
+    h = table.shape[1]
+    out = torch.empty((hp * wp, h), dtype=table.dtype, device=table.device)
+    c = ctx(table.device.index)
+    c.call("dk_pos_embed_crop", dtype_code(table.dtype), ptr(table), ptr(out), max_hw, hp, wp, h)
+    return out
+
+
+def copy_rows(src, dst, B: int, rows: int, h: int, dst_rows: int, dst_off: int, src_rows: int, src_off: int):
+    _chk16(src, "copy_rows.src")
+    c = ctx(src.device.index)
+    c.call("dk_copy_rows", dtype_code(src.dtype), ptr(src), ptr(dst), B, rows, h, dst_rows, dst_off, src_rows, src_off)
+    return dst
+
+
+def sampler_prepare(x, xin, reps: int):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    c = ctx(x.device.index)
+    c.call("dk_sampler_prepare", dtype_code(xin.dtype), ptr(x), ptr(xin), x.numel(), reps)
+    return xin
+
+
+def sampler_step(x, xin, out, sigma: float, sigma_next: float, cfg_weight: float):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    c = ctx(x.device.index)
+    c.call("dk_sampler_step", dtype_code(xin.dtype), ptr(x), ptr(xin), ptr(out), x.numel(), sigma, sigma_next,
+           cfg_weight)
+    return x
+
+
+def axpb(x, a: float, b: float, out=None):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    c = ctx(x.device.index)
+    c.call("dk_axpb_f32", ptr(x), ptr(out), x.numel(), a, b)
+    return out
+
+
+def cast_to_16(x, dtype, out=None):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if out is None:
+        out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    c = ctx(x.device.index)
+    c.call("dk_cast_f32_to_16", dtype_code(dtype), ptr(x), ptr(out), x.numel())
+    return out
+
+
+def cast_to_f32(x, out=None):
+    _chk16(x, "cast_to_f32.x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    c = ctx(x.device.index)
+    c.call("dk_cast_16_to_f32", dtype_code(x.dtype), ptr(x), ptr(out), x.numel())
+    return out
+
+
+def groupnorm_stats(x, G: int, eps: float = 1e-5, ws=None):
+    """x NHWC [B, H, W, C] -> stats [B, G, 2] (mean, rstd)."""
+    _chk16(x, "groupnorm_stats.x")
+    B, H, W, Cc = x.shape
+    c = ctx(x.device.index)
+    n_ws = c.lib.dk_groupnorm_ws_floats(B, G)
+    if ws is None:
+        ws = torch.empty(n_ws, dtype=torch.float32, device=x.device)
+    assert ws.numel() >= n_ws
+    stats = torch.empty((B, G, 2), dtype=torch.float32, device=x.device)
+    c.call("dk_groupnorm_stats", dtype_code(x.dtype), ptr(x), ptr(stats), ptr(ws), B, H * W, Cc, G, eps)
+    return stats
+
+
+def groupnorm_apply(x, stats, gamma, beta, G: int, silu: bool, out=None):
+    _chk16(x, "groupnorm_apply.x")
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    c = ctx(x.device.index)
+    c.call("dk_groupnorm_apply", dtype_code(x.dtype), ptr(x), ptr(out), ptr(stats), ptr(gamma), ptr(beta), B, H * W, Cc,
+           G, 1 if silu else 0)
+    return out
+
+
+def conv3x3(x, w, bias=None, res=None, out=None):
+    """x NHWC [B,H,W,Cin], w [Cout,3,3,Cin] -> NHWC [B,H,W,Cout] (+ res)."""
+    _chk16(x, "conv3x3.x")
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, 3, 3, Cin) and x.is_contiguous() and w.is_contiguous()
+    if out is None:
+        out = torch.empty((B, H, W, Cout), dtype=x.dtype, device=x.device)
+    c = ctx(x.device.index)
+    c.call("dk_conv3x3", dtype_code(x.dtype), ptr(x), ptr(w), ptr(bias), ptr(res), ptr(out), B, H, W, Cin, Cout)
+    return out
+
+
+def upsample_nearest2x(x, out=None):
+    _chk16(x, "upsample.x")
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=x.dtype, device=x.device)
+    c = ctx(x.device.index)
+    c.call("dk_upsample_nearest2x", dtype_code(x.dtype), ptr(x), ptr(out), B, H, W, Cc)
+    return out
+
+
+def softmax_rows(x, scale: float = 1.0):
+    _chk16(x, "softmax_rows.x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    c = ctx(x.device.index)
+    c.call("dk_softmax_rows", dtype_code(x.dtype), ptr(x), x.shape[0], x.shape[1], x.stride(0), scale)
+    return x
+
+
+def image_post(x, want_u8: bool = True):
+    """decoder output NHWC [B,H,W,Cpad] -> (float [B,H,W,3] in [0,1], uint8 [B,H,W,3])."""
+    _chk16(x, "image_post.x")
+    B, H, W, Cp = x.shape
+    f = torch.empty((B, H, W, 3), dtype=torch.float32, device=x.device)
+    u = torch.empty((B, H, W, 3), dtype=torch.uint8, device=x.device) if want_u8 else None
+    c = ctx(x.device.index)
+    c.call("dk_image_post", dtype_code(x.dtype), ptr(x), Cp, ptr(f), ptr(u), B * H * W)
+    return f, u

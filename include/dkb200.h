@@ -1,0 +1,188 @@
+/* dkb200 — C ABI of the B200-native denoise + decode engine behind DiffusionKit's
+ * `diffusionkit.mlx` DiffusionPipeline / FluxPipeline API.
+ *
+ * The reference (argmaxinc/DiffusionKit @ 498e5dba) has no FFI boundary: its hot path sits behind a
+ * Python class API and bottoms out in MLX library calls.  This header is the boundary a maintainer
+ * would bind instead (ctypes stub in INTEGRATION.md).  Each entry point cites the reference code it
+ * replaces (paths relative to python/src/diffusionkit/mlx/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; dk_last_error() gives the message
+ *     (thread-local).  No C++ exception crosses this boundary.
+ *   - all pointers are DEVICE pointers unless a name ends in _host; buffers are caller-owned
+ *     (torch tensors on the Python side); the library borrows them for the duration of a call
+ *     (weights: until the model handle is destroyed).
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *   - dtype: DK_BF16 (FLUX: __init__.py:610) or DK_FP16 (SD3: __init__.py:76) for weights and
+ *     activations; sampler state is fp32 (__init__.py:761-788).
+ *   - layouts follow the reference: latents/images NHWC (mmdit.py:188-266, vae.py:386-401),
+ *     Linear weights (out,in) (mlx nn.Linear), conv weights (O,kh,kw,I) (mlx nn.Conv2d).
+ */
+#ifndef DKB200_H
+#define DKB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DK_BF16 0
+#define DK_FP16 1
+
+#define DK_ACT_NONE 0
+#define DK_ACT_GELU_ERF 1 /* mlx nn.GELU() exact erf — mmdit.py:421,835 */
+#define DK_ACT_SILU 2
+
+typedef struct dk_ctx dk_ctx;
+
+const char* dk_version(void);
+const char* dk_last_error(void);
+int dk_ctx_create(int device, dk_ctx** out);
+void dk_ctx_destroy(dk_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+long long dk_ctx_launch_count(dk_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  tcgen05 GEMM with fused epilogue — replaces every nn.Linear on the path
+ *     (mmdit.py:471-473 q/k/v, :532 o_proj, :830-835 FFN, :430-435 adaLN, :56-59 context_embedder,
+ *      :357-361/:372-376 embedders, :771-774 final linear; vae.py:36-39 attention projections).
+ *     out[row(m), n] = res[rrow(m), n] + gate[m / rows_per_batch, n] * act(sum_k A[m,k] W[n,k] + bias[n])
+ *     row(m)  = (m / rows_per_batch) * out_batch_rows + out_row_off + m % rows_per_batch
+ *     rrow(m) = (m / rows_per_batch) * res_batch_rows + res_row_off + m % rows_per_batch
+ *     (the row maps let a stream's GEMM write straight into the joint [text|image] sequence buffer,
+ *      mmdit.py:594-625, and let a per-position table broadcast over the batch, mmdit.py:334-349.)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dk_gemm_args {
+  int dtype;
+  int M, N, K;
+  const void* A; /* [M, K] row-major, leading dim lda (elements) */
+  long long lda;
+  const void* W; /* [N, K] row-major (nn.Linear weight), leading dim ldw; if w_n_major: [K, N] */
+  long long ldw;
+  void* out; /* 16-bit output */
+  long long ldc;
+  const void* bias; /* [N] or NULL */
+  const void* gate; /* [batches, gate_ld] or NULL */
+  long long gate_ld;
+  const void* res; /* residual or NULL (may alias out) */
+  long long ldres;
+  int rows_per_batch; /* 0 => M */
+  int out_batch_rows, out_row_off;
+  int res_batch_rows, res_row_off;
+  int act;       /* DK_ACT_* applied to (acc + bias) */
+  int w_n_major; /* 1: W is [K, N] row-major (exercises the MN-major operand path used for V) */
+} dk_gemm_args;
+int dk_gemm(dk_ctx* ctx, const dk_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  LayerNorm (no affine, eps) + adaLN modulate: y = LN(x) * (1 + scale[b]) + shift[b]
+ *     replaces affine_transform / mx.fast.layer_norm — mmdit.py:958-972, :838-849.
+ *     x, y: [B*rows_per_batch, h]; shift/scale: row b at ptr + b*mod_ld (16-bit).
+ * ------------------------------------------------------------------------------------------- */
+int dk_ln_modulate(dk_ctx* ctx, int dtype, const void* x, void* y, const void* shift, const void* scale,
+                   long long mod_ld, int rows, int rows_per_batch, int h, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * QK-RMSNorm (mmdit.py:754-764, eps 1e-6, learned weight) + FLUX RoPE (mmdit.py:934-942) applied
+ * in place to the q and k thirds of a packed [rows, 3h] QKV buffer.
+ *   rows = B * S; row r -> sequence position r % S.
+ *   q_w/k_w: norm weights [d] for positions < split, q_w2/k_w2 for positions >= split (the text and
+ *   image streams of a MultiModalTransformerBlock own separate QKNorm modules); NULL => no norm.
+ *   rope: fp32 [S, d/2, 2] (cos, sin) or NULL (SD3: no RoPE).
+ * ------------------------------------------------------------------------------------------- */
+int dk_qk_norm_rope(dk_ctx* ctx, int dtype, void* qkv, int rows, int S, int heads, int d, int split, const void* q_w,
+                    const void* k_w, const void* q_w2, const void* k_w2, const float* rope, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  attention forward: softmax(scale * Q K^T) V, no mask — replaces
+ *     mx.fast.scaled_dot_product_attention (mmdit.py:562-563,643,687-688,736).
+ *     qkv: packed [B*S, 3*heads*d] (q | k | v thirds, head-major inside a third).
+ *     output row (b, s): s < split -> out0[(b*split + s) * ld0 + head*d ...]
+ *                        else      -> out1[(b*(S-split) + s-split) * ld1 + head*d ...]
+ *     (split = S with out1 = NULL writes one [B*S, ld0] buffer.)  d in {64, 128}.
+ * ------------------------------------------------------------------------------------------- */
+int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, int S, int heads, int d, float scale, int split,
+                     void* out0, long long ld0, void* out1, long long ld1, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * elementwise / layout kernels on the MMDiT path
+ * ------------------------------------------------------------------------------------------- */
+/* c[t*B + b, :] = silu(y[b, :] + temb[t, :])  — input of every adaLN Linear (mmdit.py:94-96, :430-431) */
+int dk_silu_add(dk_ctx* ctx, int dtype, const void* y, const void* temb, void* c, int n_t, int B, int h, void* stream);
+/* act(x) elementwise, 16-bit (MLP embedders: mmdit.py:357-361, :372-376) */
+int dk_act(dk_ctx* ctx, int dtype, const void* x, void* y, long long n, int act, void* stream);
+/* latent NHWC (B,H,W,C) 16-bit -> patch rows [B*(H/2)*(W/2), 4C].
+ * order 0: (c, ph, pw)  FLUX reshape patchify (mmdit.py:292-302)
+ * order 1: (ph, pw, c)  SD3 conv k2 s2 im2col, matches weight (O,kh,kw,I) (mmdit.py:285-290) */
+int dk_patchify(dk_ctx* ctx, int dtype, const void* latent, void* rows, int B, int H, int W, int C, int order,
+                void* stream);
+/* rows [B*(H/2)*(W/2), 4C] 16-bit -> NHWC (B,H,W,C) 16-bit.  order 0: FLUX unpack (mmdit.py:304-321);
+ * order 1: SD3 unpatchify (p, q, c) (mmdit.py:975-988) */
+int dk_unpatchify(dk_ctx* ctx, int dtype, const void* rows, void* latent, int B, int H, int W, int C, int order,
+                  void* stream);
+/* crop of the learned position table (mmdit.py:334-349): table [max_hw*max_hw, h] -> out [hp*wp, h] */
+int dk_pos_embed_crop(dk_ctx* ctx, int dtype, const void* table, void* out, int max_hw, int hp, int wp, int h,
+                      void* stream);
+/* copy [B, rows, h] blocks into a wider sequence buffer: dst[b, dst_off + r, :] = src[b, r, :] */
+int dk_copy_rows(dk_ctx* ctx, int dtype, const void* src, void* dst, int B, int rows, int h, int dst_rows, int dst_off,
+                 int src_rows, int src_off, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K6  sampler step (fp32 state) — CFGDenoiser + Euler update, __init__.py:691-719, :775-782,
+ *     sampler.py:37-39.
+ *   dk_sampler_prepare: xin[(k*B + b)] = cast16(x[b]) for k in 0..reps-1  (reps = 2 when cfg > 0, :700-706)
+ *   dk_sampler_step:    den = float(xin) - float(out) * sigma; if cfg: den = den_neg + w (den_text - den_neg)
+ *                       x += ((x - den) / sigma) * (sigma_next - sigma)
+ * ------------------------------------------------------------------------------------------- */
+int dk_sampler_prepare(dk_ctx* ctx, int dtype, const float* x, void* xin, long long n_per_rep, int reps, void* stream);
+int dk_sampler_step(dk_ctx* ctx, int dtype, float* x, const void* xin, const void* out, long long n, float sigma,
+                    float sigma_next, float cfg_weight, void* stream);
+/* y = x * a + b (fp32): latent_format.process_out (__init__.py:732-733) and noise scaling (sampler.py:41-42) */
+int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, float a, float b, void* stream);
+/* fp32 <-> 16-bit casts */
+int dk_cast_f32_to_16(dk_ctx* ctx, int dtype, const float* x, void* y, long long n, void* stream);
+int dk_cast_16_to_f32(dk_ctx* ctx, int dtype, const void* x, float* y, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * VAE decoder kernels (vae.py:20-149, 336-401)
+ * ------------------------------------------------------------------------------------------- */
+/* K7a GroupNorm statistics (nn.GroupNorm(32, C, pytorch_compatible=True), eps 1e-5; vae.py:34,72,78):
+ *     stats[(b*G + g)*2 + {0,1}] = mean, rstd over (H*W, C/G); x NHWC 16-bit.
+ *     ws: scratch of dk_groupnorm_ws_floats(B, G) floats (two-stage deterministic reduction, no atomics). */
+int dk_groupnorm_ws_floats(int B, int G);
+int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* stats, float* ws, int B, int HW, int C, int G,
+                       float eps, void* stream);
+/* GroupNorm apply (+ optional SiLU): y = act((x - mean) * rstd * gamma[c] + beta[c]) */
+int dk_groupnorm_apply(dk_ctx* ctx, int dtype, const void* x, void* y, const float* stats, const void* gamma,
+                       const void* beta, int B, int HW, int C, int G, int silu, void* stream);
+/* K7  conv 3x3, stride 1, zero pad 1, NHWC, as an im2col-free implicit GEMM: the 9 taps are 9 shifted TMA
+ *     boxes of the input (out-of-bounds = zero fill = the padding), accumulated in TMEM.
+ *     x [B,H,W,Cin] (Cin % 64 == 0), w [Cout,3,3,Cin] (Cout % 8 == 0), bias [Cout], res NHWC [B,H,W,Cout] or NULL
+ *     (the ResnetBlock2D skip, vae.py:99).  replaces nn.Conv2d 3x3 (vae.py:73-81,134-136,349-351,384) */
+int dk_conv3x3(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, const void* res, void* out,
+               int B, int H, int W, int Cin, int Cout, void* stream);
+/* nearest 2x upsample NHWC (vae.py:20-25) */
+int dk_upsample_nearest2x(dk_ctx* ctx, int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
+/* row softmax in place: x[r, :n] = softmax(scale * x[r, :n]); fp32 math, 16-bit storage (vae.py:49-52) */
+int dk_softmax_rows(dk_ctx* ctx, int dtype, void* x, long long rows, int n, long long ld, float scale, void* stream);
+/* clip(x/2 + 0.5, 0, 1) (and optional trunc(x*255) -> uint8): __init__.py:583, :526.
+ * x NHWC [.., C_in_stride] 16-bit, takes the first 3 channels. */
+int dk_image_post(dk_ctx* ctx, int dtype, const void* x, int c_stride, float* img_f32, uint8_t* img_u8, long long pixels,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * one-time weight broadcast for multi-GPU batch sharding (no per-step collective).
+ * The Python host uses torch.distributed (NCCL) for the rendezvous; these are thin NCCL wrappers
+ * for hosts without torch.
+ * ------------------------------------------------------------------------------------------- */
+int dk_comm_unique_id(uint8_t id_host[128]);
+int dk_comm_init(dk_ctx* ctx, int rank, int world, const uint8_t id_host[128]);
+int dk_comm_broadcast(dk_ctx* ctx, void* ptr, size_t bytes, int root, void* stream);
+int dk_comm_destroy(dk_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DKB200_H */

@@ -1,0 +1,403 @@
+"""GPU checks of the individual sm_100a kernels against plain fp32 torch references of the same op.
+
+Each check_* function is self-contained (used by tests/test_kernels_gpu.py and by tools/run_gpu_checks.py, which
+runs every check in its own process so that one trapped kernel cannot poison the others).
+Tolerances: 16-bit outputs, fp32 accumulation -> relative L2 error <= 4e-3 (bf16 epsilon is 3.9e-3 per element,
+the L2 over many elements averages to ~2e-3); attention <= 1e-2.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+from diffusionkit_b200 import ops
+from diffusionkit_b200._lib import ACT_GELU_ERF, ACT_NONE, ACT_SILU
+
+DEV = "cuda:0"
+
+
+def _setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.manual_seed(0)
+
+
+def rel_l2(a, b):
+    a = a.float()
+    b = b.float()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _dump(name, **arrs):
+    d = os.environ.get("DK_DUMP_DIR")
+    if not d:
+        return
+    os.makedirs(d, exist_ok=True)
+    np.savez_compressed(os.path.join(d, name + ".npz"), **{k: v.float().cpu().numpy() for k, v in arrs.items()})
+
+
+def _assert_close(name, got, ref, tol):
+    err = rel_l2(got, ref)
+    finite = bool(torch.isfinite(got.float()).all())
+    if not finite or not err <= tol:
+        _dump(name, got=got, ref=ref)
+        raise AssertionError(f"{name}: rel_l2={err:.3e} (tol {tol:.1e}) finite={finite}")
+    return err
+
+
+def _rand(shape, dtype, scale=1.0):
+    return (torch.randn(shape, device=DEV, dtype=torch.float32) * scale).to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def _gemm_case(M, N, K, dtype, bias=False, act=ACT_NONE, gate=False, res=False, remap=False, name=""):
+    A = _rand((M, K), dtype)
+    W = _rand((N, K), dtype, 1.0 / math.sqrt(K))
+    b = _rand((N,), dtype, 0.5) if bias else None
+    ref = A.float() @ W.float().t()
+    if bias:
+        ref = ref + b.float()
+    if act == ACT_GELU_ERF:
+        ref = torch.nn.functional.gelu(ref)
+    elif act == ACT_SILU:
+        ref = torch.nn.functional.silu(ref)
+    kw = {}
+    out = None
+    if remap:
+        # M = Bt * rpb rows scattered into a [Bt * out_rows, N] buffer at row offset off
+        Bt = 2
+        assert M % Bt == 0
+        rpb = M // Bt
+        out_rows, off = rpb + 40, 24
+        out = torch.zeros((Bt * out_rows, N), dtype=dtype, device=DEV)
+        kw.update(rows_per_batch=rpb, out_batch_rows=out_rows, out_row_off=off)
+        g = _rand((Bt, N), dtype) if gate else None
+        r = _rand((Bt * rpb, N), dtype) if res else None
+        if gate:
+            ref = ref * g.float().repeat_interleave(rpb, 0)
+        if res:
+            ref = ref + r.float()
+        got = ops.gemm(A, W, out=out, bias=b, act=act, gate=g, res=r, **kw)
+        got_rows = torch.cat([got[i * out_rows + off:i * out_rows + off + rpb] for i in range(Bt)], 0)
+        untouched = torch.cat([got[i * out_rows:i * out_rows + off] for i in range(Bt)], 0)
+        assert float(untouched.float().abs().max()) == 0.0, f"{name}: rows outside the remap window were written"
+        return _assert_close(name, got_rows, ref, 4e-3)
+    g = _rand((1, N), dtype) if gate else None
+    r = _rand((M, N), dtype) if res else None
+    if gate:
+        ref = ref * g.float()
+    if res:
+        ref = ref + r.float()
+    got = ops.gemm(A, W, bias=b, act=act, gate=g, res=r)
+    return _assert_close(name, got, ref, 4e-3)
+
+
+def check_gemm_single_tile():
+    _setup()
+    return {"err": _gemm_case(128, 256, 64, torch.bfloat16, name="gemm_128x256x64")}
+
+
+def check_gemm_multi_k():
+    _setup()
+    return {"err": _gemm_case(128, 256, 512, torch.bfloat16, name="gemm_128x256x512")}
+
+
+def check_gemm_shapes():
+    _setup()
+    out = {}
+    for (M, N, K) in [(256, 512, 256), (300, 264, 200), (77, 64, 64), (1000, 3072, 1536), (20, 1024, 3072),
+                      (4352, 768, 3072), (128, 128, 128)]:
+        out[f"{M}x{N}x{K}"] = _gemm_case(M, N, K, torch.bfloat16, name=f"gemm_{M}x{N}x{K}")
+    return out
+
+
+def check_gemm_persistent_large():
+    _setup()
+    # more tiles than SMs: exercises the persistent loop, both TMEM accumulators and the smem ring wrap-around
+    return {"err": _gemm_case(4096, 4608, 1024, torch.bfloat16, bias=True, name="gemm_4096x4608x1024")}
+
+
+def check_gemm_epilogues():
+    _setup()
+    out = {}
+    out["bias"] = _gemm_case(384, 512, 256, torch.bfloat16, bias=True, name="gemm_bias")
+    out["gelu"] = _gemm_case(384, 512, 256, torch.bfloat16, bias=True, act=ACT_GELU_ERF, name="gemm_gelu")
+    out["silu"] = _gemm_case(384, 512, 256, torch.bfloat16, bias=True, act=ACT_SILU, name="gemm_silu")
+    out["gate_res"] = _gemm_case(384, 512, 256, torch.bfloat16, bias=True, gate=True, res=True, name="gemm_gate_res")
+    out["remap"] = _gemm_case(600, 512, 256, torch.bfloat16, bias=True, gate=True, res=True, remap=True,
+                              name="gemm_remap")
+    return out
+
+
+def check_gemm_fp16():
+    _setup()
+    return {"err": _gemm_case(300, 512, 320, torch.float16, bias=True, act=ACT_GELU_ERF, name="gemm_fp16")}
+
+
+def check_gemm_inplace_residual():
+    _setup()
+    M, N, K = 256, 256, 128
+    A = _rand((M, K), torch.bfloat16)
+    W = _rand((N, K), torch.bfloat16, 1 / math.sqrt(K))
+    x = _rand((M, N), torch.bfloat16)
+    ref = x.float() + A.float() @ W.float().t()
+    got = ops.gemm(A, W, out=x, res=x)
+    return {"err": _assert_close("gemm_inplace", got, ref, 4e-3)}
+
+
+def check_gemm_w_n_major():
+    _setup()
+    out = {}
+    for (M, N, K) in [(128, 128, 64), (256, 384, 256), (200, 136, 72)]:
+        A = _rand((M, K), torch.bfloat16)
+        Wt = _rand((K, N), torch.bfloat16, 1 / math.sqrt(K))  # [K, N] row-major
+        ref = A.float() @ Wt.float()
+        got = ops.gemm(A, Wt, w_n_major=True)
+        out[f"{M}x{N}x{K}"] = _assert_close(f"gemm_nmajor_{M}x{N}x{K}", got, ref, 4e-3)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def _conv_case(B, H, W, Cin, Cout, dtype, bias=True, res=False, name=""):
+    x = _rand((B, H, W, Cin), dtype)
+    w = _rand((Cout, 3, 3, Cin), dtype, 1 / math.sqrt(9 * Cin))
+    b = _rand((Cout,), dtype, 0.5) if bias else None
+    r = _rand((B, H, W, Cout), dtype) if res else None
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2),
+                                     b.float() if bias else None, padding=1).permute(0, 2, 3, 1)
+    if res:
+        ref = ref + r.float()
+    got = ops.conv3x3(x, w, bias=b, res=r)
+    return _assert_close(name, got, ref, 4e-3)
+
+
+def check_conv3x3():
+    _setup()
+    out = {}
+    out["16x16"] = _conv_case(2, 16, 16, 64, 64, torch.bfloat16, name="conv_16x16")
+    out["8x32_res"] = _conv_case(1, 8, 32, 128, 128, torch.bfloat16, res=True, name="conv_8x32")
+    out["12x20_ragged"] = _conv_case(2, 12, 20, 64, 72, torch.bfloat16, name="conv_12x20")
+    out["64x256"] = _conv_case(1, 64, 256, 128, 256, torch.bfloat16, res=True, name="conv_64x256")
+    out["fp16"] = _conv_case(1, 32, 32, 64, 16, torch.float16, name="conv_fp16")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _attention_case(B, S, heads, d, dtype, split=None, name=""):
+    h = heads * d
+    qkv = _rand((B * S, 3 * h), dtype)
+    q, k, v = [t.reshape(B, S, heads, d).permute(0, 2, 1, 3).float() for t in qkv.split(h, dim=1)]
+    ref = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1) @ v
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, h)
+    if split is None:
+        out = torch.zeros((B * S, h), dtype=dtype, device=DEV)
+        ops.attention(qkv, B, S, heads, d, out)
+        got = out.reshape(B, S, h)
+    else:
+        o0 = torch.zeros((B * split, h), dtype=dtype, device=DEV)
+        o1 = torch.zeros((B * (S - split), h + 64), dtype=dtype, device=DEV)[:, :h]  # non-trivial leading dim
+        ops.attention(qkv, B, S, heads, d, o0, split=split, out1=o1)
+        got = torch.cat([o0.reshape(B, split, h), o1.reshape(B, S - split, h)], dim=1)
+    return _assert_close(name, got, ref, 1e-2)
+
+
+def check_attention_d128_one_tile():
+    _setup()
+    return {"err": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att_d128_S128")}
+
+
+def check_attention_d128():
+    _setup()
+    out = {}
+    out["S300"] = _attention_case(2, 300, 2, 128, torch.bfloat16, name="att_d128_S300")
+    out["S1280_split"] = _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att_d128_S1280")
+    return out
+
+
+def check_attention_d64():
+    _setup()
+    out = {}
+    out["S128"] = _attention_case(1, 128, 1, 64, torch.float16, name="att_d64_S128")
+    out["S1178_split"] = _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att_d64_S1178")
+    out["bf16_S333"] = _attention_case(1, 333, 2, 64, torch.bfloat16, name="att_d64_S333")
+    return out
+
+
+def check_attention_large_scores():
+    """rows whose running max keeps growing: exercises the lazy O rescale path."""
+    _setup()
+    B, S, heads, d = 1, 1024, 1, 128
+    h = heads * d
+    qkv = _rand((B * S, 3 * h), torch.bfloat16)
+    # make later keys progressively more aligned with the queries
+    ramp = torch.linspace(0.2, 6.0, S, device=DEV).unsqueeze(1)
+    base = _rand((1, d), torch.bfloat16).float()
+    qkv[:, :h] = (base * 2.0 + 0.3 * qkv[:, :h].float()).to(torch.bfloat16)
+    qkv[:, h:2 * h] = (base * ramp + 0.3 * qkv[:, h:2 * h].float()).to(torch.bfloat16)
+    q, k, v = [t.reshape(B, S, heads, d).permute(0, 2, 1, 3).float() for t in qkv.split(h, dim=1)]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(d), dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, h)
+    out = torch.zeros((B * S, h), dtype=torch.bfloat16, device=DEV)
+    ops.attention(qkv, B, S, heads, d, out)
+    return {"err": _assert_close("att_rescale", out, ref, 1e-2)}
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def check_ln_modulate():
+    _setup()
+    out = {}
+    for (B, S, h, dt) in [(2, 37, 3072, torch.bfloat16), (1, 64, 1536, torch.float16), (3, 5, 128, torch.bfloat16)]:
+        x = _rand((B * S, h), dt, 2.0) + 0.5
+        mod = _rand((B, 6 * h), dt, 0.3)
+        shift, scale = mod[:, 0:h], mod[:, h:2 * h]
+        xf = x.float()
+        ln = torch.nn.functional.layer_norm(xf, (h,), eps=1e-6)
+        ref = ln * (1 + scale.float().repeat_interleave(S, 0)) + shift.float().repeat_interleave(S, 0)
+        got = ops.ln_modulate(x, shift, scale, S, 1e-6)
+        out[f"{B}x{S}x{h}"] = _assert_close(f"ln_{h}", got, ref, 4e-3)
+    return out
+
+
+def _rope_table(S, d, device):
+    ang = torch.rand((S, d // 2), device=device) * 6.28
+    return torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous()
+
+
+def check_qk_norm_rope():
+    _setup()
+    out = {}
+    for (B, S, heads, d, dt, use_norm, use_rope) in [(2, 50, 3, 128, torch.bfloat16, True, True),
+                                                     (1, 33, 2, 64, torch.float16, True, False),
+                                                     (1, 40, 2, 128, torch.bfloat16, False, True)]:
+        h = heads * d
+        qkv = _rand((B * S, 3 * h), dt)
+        split = S // 3
+        ws = [(_rand((d,), dt, 0.1) + 1.0) for _ in range(4)] if use_norm else [None] * 4
+        rope = _rope_table(S, d, DEV) if use_rope else None
+        ref = qkv.float().clone()
+        pos = torch.arange(B * S, device=DEV) % S
+        for which, (w1, w2) in enumerate([(ws[0], ws[2]), (ws[1], ws[3])]):
+            t = ref[:, which * h:(which + 1) * h].reshape(B * S, heads, d)
+            if use_norm:
+                w = torch.where((pos < split)[:, None, None], w1.float()[None, None], w2.float()[None, None])
+                t = t * torch.rsqrt((t * t).mean(-1, keepdim=True) + 1e-6) * w
+                t = t.to(dt).float()
+            if use_rope:
+                c = rope[pos][:, None, :, 0]
+                s = rope[pos][:, None, :, 1]
+                x0, x1 = t[..., 0::2], t[..., 1::2]
+                t = torch.stack([x0 * c - x1 * s, x0 * s + x1 * c], dim=-1).reshape(B * S, heads, d)
+            ref[:, which * h:(which + 1) * h] = t.reshape(B * S, h)
+        got = ops.qk_norm_rope(qkv.clone(), S, heads, d, split, ws[0], ws[1], ws[2], ws[3], rope)
+        out[f"d{d}_{use_norm}_{use_rope}"] = _assert_close(f"qknr_{d}", got, ref, 4e-3)
+    return out
+
+
+def check_layout_kernels():
+    _setup()
+    out = {}
+    dt = torch.bfloat16
+    B, H, W, Cc = 2, 8, 12, 16
+    lat = _rand((B, H, W, Cc), dt)
+    # FLUX order (c, ph, pw) — reference mmdit.py:292-302
+    ref0 = lat.reshape(B, H // 2, 2, W // 2, 2, Cc).permute(0, 1, 3, 5, 2, 4).reshape(B * (H // 2) * (W // 2), 4 * Cc)
+    got0 = ops.patchify(lat, 0)
+    assert torch.equal(got0, ref0), "patchify order 0"
+    # SD3 order (ph, pw, c)
+    ref1 = lat.reshape(B, H // 2, 2, W // 2, 2, Cc).permute(0, 1, 3, 2, 4, 5).reshape(B * (H // 2) * (W // 2), 4 * Cc)
+    got1 = ops.patchify(lat, 1)
+    assert torch.equal(got1, ref1), "patchify order 1"
+    assert torch.equal(ops.unpatchify(got0, B, H, W, Cc, 0), lat), "unpatchify order 0"
+    assert torch.equal(ops.unpatchify(got1, B, H, W, Cc, 1), lat), "unpatchify order 1"
+    # pos-embed crop — reference mmdit.py:334-349
+    max_hw, hp, wp, h = 12, 4, 6, 64
+    table = _rand((max_hw * max_hw, h), dt)
+    y0, x0 = (max_hw - hp) // 2, (max_hw - wp) // 2
+    refc = table.reshape(max_hw, max_hw, h)[y0:y0 + hp, x0:x0 + wp].reshape(hp * wp, h)
+    assert torch.equal(ops.pos_embed_crop(table, max_hw, hp, wp), refc), "pos_embed_crop"
+    # copy_rows
+    src = _rand((2, 5, 64), dt)
+    dst = torch.zeros((2, 9, 64), dtype=dt, device=DEV)
+    ops.copy_rows(src, dst, 2, 5, 64, 9, 3, 5, 0)
+    assert torch.equal(dst[:, 3:8], src) and float(dst[:, :3].float().abs().max()) == 0
+    # silu_add / act
+    y = _rand((3, 128), dt)
+    temb = _rand((4, 128), dt)
+    refs = torch.nn.functional.silu((y.float()[None] + temb.float()[:, None]).to(dt).float()).reshape(12, 128)
+    out["silu_add"] = _assert_close("silu_add", ops.silu_add(y, temb), refs, 4e-3)
+    out["act_silu"] = _assert_close("act_silu", ops.act(y, ACT_SILU), torch.nn.functional.silu(y.float()), 4e-3)
+    # upsample
+    x = _rand((2, 3, 5, 16), dt)
+    refu = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    assert torch.equal(ops.upsample_nearest2x(x), refu), "upsample"
+    return out
+
+
+def check_sampler_kernels():
+    _setup()
+    dt = torch.bfloat16
+    n = 2 * 8 * 8 * 16
+    x = torch.randn(n, device=DEV)
+    out = {}
+    for cfg in (0.0, 5.0):
+        reps = 2 if cfg > 0 else 1
+        xin = torch.empty(reps * n, dtype=dt, device=DEV)
+        ops.sampler_prepare(x, xin, reps)
+        assert torch.equal(xin[:n], x.to(dt)) and torch.equal(xin[-n:], x.to(dt))
+        mo = _rand((reps * n,), dt)
+        sigma, sigma_next = 0.75, 0.5
+        den = xin.float() - mo.float() * sigma
+        if cfg > 0:
+            den = den[n:] + cfg * (den[:n] - den[n:])
+        ref = x + (x - den) / sigma * (sigma_next - sigma)
+        got = ops.sampler_step(x.clone(), xin, mo, sigma, sigma_next, cfg)
+        out[f"cfg{cfg}"] = _assert_close(f"sampler_{cfg}", got, ref, 1e-5)
+    out["axpb"] = _assert_close("axpb", ops.axpb(x, 1 / 0.3611, 0.1159), x / 0.3611 + 0.1159, 1e-6)
+    assert torch.equal(ops.cast_to_16(x, dt), x.to(dt))
+    assert torch.equal(ops.cast_to_f32(x.to(dt)), x.to(dt).float())
+    return out
+
+
+def check_groupnorm():
+    _setup()
+    out = {}
+    for (B, H, W, Cc, dt) in [(2, 16, 16, 128, torch.bfloat16), (1, 9, 7, 512, torch.bfloat16),
+                              (1, 32, 32, 256, torch.float16)]:
+        x = _rand((B, H, W, Cc), dt, 1.5) + 0.7
+        gamma = _rand((Cc,), dt, 0.1) + 1.0
+        beta = _rand((Cc,), dt, 0.1)
+        stats = ops.groupnorm_stats(x, 32, 1e-5)
+        xf = x.float().reshape(B, H * W, 32, Cc // 32)
+        mean = xf.mean(dim=(1, 3))
+        var = xf.var(dim=(1, 3), unbiased=False)
+        out[f"stats_{Cc}"] = _assert_close("gn_mean", stats[..., 0], mean, 1e-4)
+        _assert_close("gn_rstd", stats[..., 1], torch.rsqrt(var + 1e-5), 1e-4)
+        ref = torch.nn.functional.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma.float(), beta.float(), 1e-5)
+        ref = torch.nn.functional.silu(ref.permute(0, 2, 3, 1).to(dt).float())
+        got = ops.groupnorm_apply(x, stats, gamma, beta, 32, True)
+        out[f"apply_{Cc}"] = _assert_close("gn_apply", got, ref, 4e-3)
+    return out
+
+
+def check_softmax_image_post():
+    _setup()
+    dt = torch.bfloat16
+    x = _rand((37, 1024), dt, 3.0)
+    ref = torch.softmax(x.float() * 0.25, dim=-1)
+    got = ops.softmax_rows(x.clone(), 0.25)
+    out = {"softmax": _assert_close("softmax", got, ref, 4e-3)}
+    img = _rand((2, 8, 8, 8), dt, 1.5)
+    f, u = ops.image_post(img)
+    v = ((img[..., :3].float() * 0.5).to(dt).float() + 0.5).to(dt).float().clamp(0, 1)
+    assert torch.equal(f, v), "image_post float"
+    assert torch.equal(u, (v * 255).to(dt).float().to(torch.uint8)), "image_post uint8"
+    return out
+
+
+ALL_CHECKS = [
+    check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
+    check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_conv3x3,
+    check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
+    check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
+    check_softmax_image_post,
+]
