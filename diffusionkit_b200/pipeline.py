@@ -1,0 +1,405 @@
+"""DiffusionPipeline / FluxPipeline — the reference's Python surface (python/src/diffusionkit/mlx/__init__.py:64-788)
+over the B200 engine.  Same constructor arguments, method names, defaults and return structures; the denoise loop and
+the decode run entirely in the CUDA kernels of libdkb200.so.
+
+Differences that are deliberate (documented in DESIGN.md):
+  * 16-bit only (w16 = a16 = True, what the reference CLI forces, scripts/generate_images.py:117-118);
+    fp32 weights/activations raise NotImplementedError.
+  * no checkpoints exist in this sandbox: weights are the deterministic synthetic initialiser of weights.py unless a
+    `params` dict (reference parameter names) is passed.  `encode_text` (CLIP/T5) raises
+    NotImplementedError; pass `conditioning` / `pooled_conditioning` to generate_image or call denoise_latents.
+  * batch-N extension: `seed` may be a list of ints — one independent image per seed (the reference is batch 1);
+    a scalar seed behaves exactly like the reference.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import DkError
+from .config import MODEL_CONFIGS, T5_MAX_LENGTH, MMDiTConfig, VAEDecoderConfig
+from .mmdit import MMDiT
+from .sampler import FluxSampler, ModelSamplingDiscreteFlow
+from .vae import VAEDecoder
+from .weights import init_params, mmdit_param_specs, vae_decoder_param_specs
+
+MMDIT_CKPT = {  # reference mlx/__init__.py:37-44 (quantised / SD3.5 variants: SURVEY.md §8 row f4)
+    "argmaxinc/mlx-stable-diffusion-3-medium": "argmaxinc/mlx-stable-diffusion-3-medium",
+    "argmaxinc/mlx-FLUX.1-schnell": "argmaxinc/mlx-FLUX.1-schnell",
+    "argmaxinc/mlx-FLUX.1-dev": "argmaxinc/mlx-FLUX.1-dev",
+}
+
+
+class LatentFormat:
+    """Base class for latent format conversion (reference mlx/__init__.py:722-733)"""
+
+    def __init__(self):
+        self.scale_factor = 1.0
+        self.shift_factor = 0.0
+
+    def process_in(self, latent):
+        return (latent - self.shift_factor) * self.scale_factor
+
+    def process_out(self, latent):
+        return (latent / self.scale_factor) + self.shift_factor
+
+
+class SD3LatentFormat(LatentFormat):
+    def __init__(self):
+        super().__init__()
+        self.scale_factor = 1.5305
+        self.shift_factor = 0.0609
+
+
+class FluxLatentFormat(LatentFormat):
+    def __init__(self):
+        super().__init__()
+        self.scale_factor = 0.3611
+        self.shift_factor = 0.1159
+
+
+def _bytes2gigabytes(n: int) -> float:
+    return n / 1024 ** 3
+
+
+class CFGDenoiser:
+    """Helper for applying CFG scaling to diffusion outputs (reference mlx/__init__.py:674-719).
+    x_t is the fp32 sampler state on the device; one call = prepare (cast / CFG doubling) + MMDiT forward; the
+    denoised estimate and the Euler update are fused in dk_sampler_step (see sample_euler)."""
+
+    def __init__(self, model: "DiffusionPipeline"):
+        self.model = model
+
+    def cache_modulation_params(self, pooled_text_embeddings, sigmas):
+        self.model.mmdit.cache_modulation_params(pooled_text_embeddings, sigmas)
+
+    def clear_cache(self):
+        # the reference re-reads the adaLN weights it dropped (:686-689); nothing was dropped here
+        pass
+
+    def __call__(self, x_t, timestep, sigma, conditioning, cfg_weight: float = 7.5, pooled_conditioning=None):
+        m = self.model
+        reps = 1 if cfg_weight <= 0 else 2
+        B = x_t.shape[0]
+        xin = torch.empty((reps * B,) + tuple(x_t.shape[1:]), dtype=m.activation_dtype, device=x_t.device)
+        ops.sampler_prepare(x_t, xin, reps)
+        out = m.mmdit(latent_image_embeddings=xin, token_level_text_embeddings=conditioning, timestep=timestep)
+        return xin, out
+
+
+def sample_euler(model: CFGDenoiser, x, sigmas, extra_args=None):
+    """Implements Algorithm 2 (Euler steps) from Karras et al. (2022) — reference mlx/__init__.py:761-788.
+    x: (B, H, W, 16) fp32 device tensor (updated in place); sigmas: 1-D float32 numpy/torch array."""
+    extra_args = {} if extra_args is None else dict(extra_args)
+    pipe = model.model
+    sig = np.asarray(sigmas, dtype=np.float32)
+    # timesteps = sampler.timestep(sigmas).astype(activation_dtype)  (:769-771; quirk Q5)
+    timesteps = torch.from_numpy(np.asarray(pipe.sampler.timestep(sig), dtype=np.float32)).to(
+        pipe.activation_dtype).to(torch.float32).tolist()
+    pooled = extra_args.pop("pooled_conditioning")
+    model.cache_modulation_params(pooled, timesteps)
+    cfg_weight = float(extra_args.get("cfg_weight", 0.0))
+    conditioning = extra_args["conditioning"]
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(len(sig))]
+    events[0].record()
+    for i in range(len(sig) - 1):
+        xin, out = model(x, timesteps[i], float(sig[i]), conditioning, cfg_weight)
+        # denoised = xin - out * sigma; CFG mix; d = (x - denoised) / sigma; x += d * (sigma_next - sigma)
+        ops.sampler_step(x, xin, out, float(sig[i]), float(sig[i + 1]), cfg_weight)
+        events[i + 1].record()
+    model.clear_cache()
+    torch.cuda.current_stream().synchronize()  # the reference syncs every step (mx.eval, :782); once is enough here
+    iter_time = [round(events[i].elapsed_time(events[i + 1]) / 1e3, 3) for i in range(len(sig) - 1)]
+    return x, iter_time
+
+
+class DiffusionPipeline:
+    _default_model = "argmaxinc/mlx-stable-diffusion-3-medium"
+
+    def __init__(
+        self,
+        w16: bool = False,
+        shift: float = 1.0,
+        use_t5: bool = True,
+        model_version: str = "argmaxinc/mlx-stable-diffusion-3-medium",
+        low_memory_mode: bool = True,
+        a16: bool = False,
+        local_ckpt=None,
+        *,
+        device: Optional[Union[int, str, torch.device]] = None,
+        params: Optional[Dict[str, torch.Tensor]] = None,
+        vae_params: Optional[Dict[str, torch.Tensor]] = None,
+        mmdit_config: Optional[MMDiTConfig] = None,
+        weight_seed: int = 0,
+        load_decoder: bool = True,
+    ):
+        self.float16_dtype = torch.float16                                  # :76 (quirk Q10)
+        self._setup(w16, a16, shift, model_version, low_memory_mode, local_ckpt, device, params, vae_params,
+                    mmdit_config, weight_seed, load_decoder)
+        self.use_t5 = use_t5
+        self.sampler = ModelSamplingDiscreteFlow(shift=shift)
+        self.latent_format = SD3LatentFormat()
+        self.use_clip_g = True
+
+    def _setup(self, w16, a16, shift, model_version, low_memory_mode, local_ckpt, device, params, vae_params,
+               mmdit_config, weight_seed, load_decoder):
+        self.mmdit_ckpt = MMDIT_CKPT[model_version]                          # KeyError on unknown model (:81)
+        if not (w16 and a16):
+            raise NotImplementedError(
+                "the B200 engine computes in 16-bit only: pass w16=True, a16=True (what the reference CLI forces, "
+                "scripts/generate_images.py:117-118)")
+        if local_ckpt is not None:
+            raise NotImplementedError("checkpoint loading (mlx/model_io.py) is SURVEY.md §8 row f1; pass `params`")
+        self.dtype = self.float16_dtype
+        self.activation_dtype = self.float16_dtype
+        self.low_memory_mode = low_memory_mode
+        self.model_version = model_version
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if device is None:
+            raise DkError("no CUDA device: diffusionkit_b200 runs on B200 only; there is no CPU fallback")
+        self.device = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        self.config = mmdit_config if mmdit_config is not None else MODEL_CONFIGS[model_version]
+        self._weight_seed = weight_seed
+        self._params, self._vae_params = params, vae_params
+        self._load_decoder = load_decoder
+        self.check_and_load_models()
+
+    # ------------------------------------------------------------------ model loading (:90-143)
+    def load_mmdit(self, only_modulation_dict=False):
+        params = self._params
+        if params is None:
+            params = init_params(mmdit_param_specs(self.config), seed=self._weight_seed, dtype=self.dtype,
+                                 device=self.device)
+        self.mmdit = MMDiT(self.config, params, device=self.device)
+
+    def check_and_load_models(self):
+        if not hasattr(self, "mmdit"):
+            self.load_mmdit()
+        if not hasattr(self, "decoder") and self._load_decoder:
+            vp = self._vae_params
+            if vp is None:
+                vp = init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=self._weight_seed + 1,
+                                 dtype=self.dtype, device=self.device)
+            self.decoder = VAEDecoder(vp, VAEDecoderConfig(), device=self.device)
+
+    # ------------------------------------------------------------------ text (row f2: not on the hot path)
+    def encode_text(self, text: str, cfg_weight: float = 7.5, negative_text: str = ""):
+        raise NotImplementedError(
+            "text encoders (CLIP-L/G, T5-XXL; reference mlx/clip.py, mlx/t5.py) are outside the denoise+decode hot "
+            "path (SURVEY.md §8 row f2): pass `conditioning` / `pooled_conditioning`, or use "
+            "synthetic_text_embeddings()")
+
+    def text_shapes(self, cfg_weight: float) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+        """(conditioning (Bc, T, 4096), pooled (Bc, P)) shapes the reference produces for ONE image."""
+        c = self.config
+        if isinstance(self, FluxPipeline):
+            return (1, T5_MAX_LENGTH.get(self.model_version, 256), c.token_level_text_embed_dim), (
+                1, c.pooled_text_embed_dim)
+        T = 77 + (T5_MAX_LENGTH.get(self.model_version, 512) if self.use_t5 else 77)    # :186-187, :239-249 (Q2)
+        return (2, T, c.token_level_text_embed_dim), (2, c.pooled_text_embed_dim)        # always 2 (Q11)
+
+    def synthetic_text_embeddings(self, n_images: int = 1, seed: int = 1234, text_len: Optional[int] = None):
+        """N(0,1) stand-ins for encode_text's outputs, laid out [positive(n) | negative(n)] for SD3."""
+        (bc, T, E), (_, P) = self.text_shapes(1.0)
+        if text_len is not None:
+            T = text_len
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        cond = torch.randn((bc * n_images, T, E), generator=g, dtype=torch.float32)
+        pooled = torch.randn((bc * n_images, P), generator=g, dtype=torch.float32)
+        return cond.to(self.activation_dtype), pooled.to(self.activation_dtype)
+
+    # ------------------------------------------------------------------ denoise (:253-292)
+    def denoise_latents(
+        self,
+        conditioning,
+        pooled_conditioning,
+        num_steps: int = 2,
+        cfg_weight: float = 0.0,
+        latent_size: Tuple[int, int] = (64, 64),
+        seed=None,
+        image_path: Optional[str] = None,
+        denoise: float = 1.0,
+    ):
+        if image_path is not None:
+            raise NotImplementedError("img2img needs the VAE encoder (SURVEY.md §8 row f3)")
+        denoise = 1.0
+        seeds: List[int]
+        if seed is None:
+            seeds = [int(time.time())]
+        elif isinstance(seed, (list, tuple)):
+            seeds = [int(s) for s in seed]
+        else:
+            seeds = [int(seed)]
+        B = len(seeds)
+        H, W = latent_size
+        conditioning = torch.as_tensor(conditioning).to(device=self.device, dtype=self.activation_dtype)
+        pooled_conditioning = torch.as_tensor(pooled_conditioning).to(device=self.device, dtype=self.activation_dtype)
+        if conditioning.dim() == 4:
+            conditioning = conditioning.squeeze(2)
+        reps = 2 if cfg_weight > 0 else 1
+        if conditioning.shape[0] != reps * B:
+            raise DkError(
+                f"conditioning has batch {conditioning.shape[0]}, expected {reps * B} "
+                f"({'[positive | negative] x ' if reps == 2 else ''}{B} image(s)) for cfg_weight={cfg_weight}")
+
+        x_T = self.get_empty_latent(H, W)                                   # (1, H, W, 16) host
+        noise = torch.cat([self.get_noise(s, x_T) for s in seeds], dim=0)   # (B, H, W, 16) host fp32
+        sigmas = self.get_sigmas(self.sampler, num_steps)
+        sigmas = sigmas[int(num_steps * (1 - denoise)):]
+        x = noise.to(self.device, non_blocking=True)
+        # noise_scaling: sigma0 * noise + (1 - sigma0) * x_T (sampler.py:41-42); x_T is the constant 0.0609
+        s0 = float(sigmas[0])
+        x = ops.axpb(x.contiguous(), s0, (1.0 - s0) * 0.0609)
+        extra_args = {"conditioning": conditioning, "cfg_weight": cfg_weight,
+                      "pooled_conditioning": pooled_conditioning}
+        latent, iter_time = sample_euler(CFGDenoiser(self), x, sigmas, extra_args=extra_args)
+        latent = ops.axpb(latent, 1.0 / self.latent_format.scale_factor, self.latent_format.shift_factor)  # process_out
+        return latent, iter_time
+
+    # ------------------------------------------------------------------ generate (:294-534)
+    def generate_image(
+        self,
+        text: str,
+        num_steps: int = 2,
+        cfg_weight: float = 0.0,
+        negative_text: str = "",
+        latent_size: Tuple[int, int] = (64, 64),
+        seed=None,
+        verbose: bool = True,
+        image_path: Optional[str] = None,
+        denoise: float = 1.0,
+        *,
+        conditioning=None,
+        pooled_conditioning=None,
+    ):
+        assert latent_size[0] % 2 == 0, f"Height must be divisible by 16 ({latent_size[0]*8}/16={latent_size[0]/2})"
+        assert latent_size[1] % 2 == 0, f"Width must be divisible by 16 ({latent_size[1]*8}/16={latent_size[1]/2})"
+        self.check_and_load_models()
+        start_time = time.time()
+
+        def mem():
+            return {"peak_memory": round(_bytes2gigabytes(torch.cuda.max_memory_allocated(self.device)), 3),
+                    "active_memory": round(_bytes2gigabytes(torch.cuda.memory_allocated(self.device)), 3)}
+
+        log = {
+            "text_encoding": {"pre": mem(), "post": {"peak_memory": None, "active_memory": None}},
+            "denoising": {"pre": {"peak_memory": None, "active_memory": None},
+                          "post": {"peak_memory": None, "active_memory": None}},
+            "decoding": {"pre": {"peak_memory": None, "active_memory": None},
+                         "post": {"peak_memory": None, "active_memory": None}},
+            "peak_memory": 0.0,
+        }
+        t0 = time.time()
+        if conditioning is None or pooled_conditioning is None:
+            conditioning, pooled_conditioning = self.encode_text(text, cfg_weight, negative_text)
+        log["text_encoding"]["post"] = mem()
+        log["text_encoding"]["time"] = round(time.time() - t0, 3)
+        log["peak_memory"] = max(log["peak_memory"], log["text_encoding"]["post"]["peak_memory"])
+
+        torch.cuda.reset_peak_memory_stats(self.device)
+        t0 = time.time()
+        log["denoising"]["pre"] = mem()
+        latents, iter_time = self.denoise_latents(conditioning, pooled_conditioning, num_steps=num_steps,
+                                                  cfg_weight=cfg_weight, latent_size=latent_size, seed=seed,
+                                                  image_path=image_path, denoise=denoise)
+        torch.cuda.synchronize(self.device)
+        log["denoising"]["post"] = mem()
+        log["denoising"]["time"] = round(time.time() - t0, 3)
+        log["denoising"]["iter_time"] = iter_time
+        log["peak_memory"] = max(log["peak_memory"], log["denoising"]["post"]["peak_memory"])
+
+        torch.cuda.reset_peak_memory_stats(self.device)
+        t0 = time.time()
+        log["decoding"]["pre"] = mem()
+        latents16 = ops.cast_to_16(latents, self.activation_dtype)          # latents.astype(activation_dtype) (:459)
+        _, u8 = self._decode(latents16, want_u8=True)
+        images_u8 = u8.cpu().numpy()                                        # device -> host: the result
+        log["decoding"]["post"] = mem()
+        log["decoding"]["time"] = round(time.time() - t0, 3)
+        log["peak_memory"] = max(log["peak_memory"], log["decoding"]["post"]["peak_memory"])
+        log["total_time"] = round(time.time() - start_time, 3)
+
+        from PIL import Image
+
+        images = [Image.fromarray(images_u8[i]) for i in range(images_u8.shape[0])]
+        # batch 1 returns a single image like the reference; a list of seeds returns a list (quirk Q9)
+        return (images[0] if not isinstance(seed, (list, tuple)) else images), log
+
+    # ------------------------------------------------------------------ helpers (:553-584)
+    def get_noise(self, seed, x_T):
+        np.random.seed(seed)
+        shape = tuple(x_T.shape)
+        noise = np.random.randn(shape[0], shape[3], shape[1], shape[2])
+        return torch.from_numpy(noise).permute(0, 2, 3, 1).to(torch.float32).contiguous()
+
+    def get_sigmas(self, sampler, num_steps: int):
+        start = float(sampler.timestep(sampler.sigma_max))
+        end = float(sampler.timestep(sampler.sigma_min))
+        if isinstance(sampler, FluxSampler):
+            num_steps += 1
+        timesteps = np.linspace(start, end, num_steps, dtype=np.float32)
+        sigs = [float(sampler.sigma(ts)) for ts in timesteps]
+        if not isinstance(sampler, FluxSampler):
+            sigs += [0.0]
+        return np.asarray(sigs, dtype=np.float32)
+
+    def get_empty_latent(self, *shape):
+        return torch.ones([1, *shape, 16], dtype=torch.float32) * 0.0609
+
+    def max_denoise(self, sigmas):
+        max_sigma = float(self.sampler.sigma_max)
+        sigma = float(sigmas[0])
+        return math.isclose(max_sigma, sigma, rel_tol=1e-05) or sigma > max_sigma
+
+    def _decode(self, x_t, want_u8: bool):
+        x = self.decoder(x_t)                                               # (B, 8H, 8W, 3) view of a padded buffer
+        B, Ho, Wo, _ = x.shape
+        padded = x.as_strided((B, Ho, Wo, x.stride(2)), (x.stride(0), x.stride(1), x.stride(2), 1))
+        return ops.image_post(padded, want_u8=want_u8)
+
+    def decode_latents_to_image(self, x_t):
+        """x = decoder(x_t); clip(x / 2 + 0.5, 0, 1)  (:581-584) -> (B, 8H, 8W, 3) float in [0, 1]"""
+        x_t = torch.as_tensor(x_t).to(device=self.device)
+        if x_t.dtype == torch.float32:
+            x_t = ops.cast_to_16(x_t.contiguous(), self.activation_dtype)
+        f, _ = self._decode(x_t, want_u8=False)
+        return f
+
+
+class FluxPipeline(DiffusionPipeline):
+    _default_model = "argmaxinc/mlx-FLUX.1-schnell"
+
+    def __init__(
+        self,
+        w16: bool = False,
+        shift: float = 1.0,
+        use_t5: bool = True,
+        model_version: str = "argmaxinc/mlx-FLUX.1-schnell",
+        low_memory_mode: bool = True,
+        a16: bool = False,
+        local_ckpt=None,
+        quantize_mmdit: bool = False,
+        *,
+        device=None,
+        params=None,
+        vae_params=None,
+        mmdit_config=None,
+        weight_seed: int = 0,
+        load_decoder: bool = True,
+    ):
+        if quantize_mmdit:
+            raise NotImplementedError("4-bit MMDiT variants are SURVEY.md §8 row f4")
+        self.float16_dtype = torch.bfloat16                                 # :610
+        self._setup(w16, a16, shift, model_version, low_memory_mode, local_ckpt, device, params, vae_params,
+                    mmdit_config, weight_seed, load_decoder)
+        self.sampler = FluxSampler(shift=shift)
+        self.latent_format = FluxLatentFormat()
+        self.use_t5 = True
+        self.use_clip_g = False
+        self.quantize_mmdit = quantize_mmdit

@@ -1,0 +1,117 @@
+"""VAE decoder on B200 — host-side mirror of the reference VAEDecoder
+(python/src/diffusionkit/mlx/vae.py:336-401; ResnetBlock2D :60-101, Attention :28-57, upsample_nearest :20-25).
+
+Same parameter names as the reference module tree.  Kernels (csrc/):
+  conv 3x3        : tcgen05 implicit GEMM, the 9 taps are shifted 4-D TMA boxes (zero fill = padding), bias and the
+                    ResNet skip fused in the epilogue
+  GroupNorm(32)   : two-stage fp32 statistics + fused normalise/affine/SiLU
+  mid attention   : q/k/v/out projections and both S=HW x HW matmuls on the tcgen05 GEMM (scores materialised like the
+                    reference, vae.py:49-52; V consumed as an MN-major operand), fp32 row softmax
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from ._lib import DkError
+from .config import VAEDecoderConfig
+
+
+def _pad_dim(t: torch.Tensor, dim: int, to: int) -> torch.Tensor:
+    if t.shape[dim] == to:
+        return t.contiguous()
+    shape = list(t.shape)
+    shape[dim] = to - t.shape[dim]
+    return torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim=dim).contiguous()
+
+
+class VAEDecoder:
+    def __init__(self, params: Dict[str, torch.Tensor], config: VAEDecoderConfig = VAEDecoderConfig(), device=None):
+        any_p = next(iter(params.values()))
+        self.device = torch.device(device) if device is not None else any_p.device
+        if self.device.type != "cuda":
+            raise DkError("VAEDecoder: parameters must live on a CUDA device (no CPU fallback)")
+        self.dtype = any_p.dtype
+        if self.dtype not in (torch.bfloat16, torch.float16):
+            raise DkError(f"VAEDecoder: weights must be bf16 or fp16, got {self.dtype}")
+        self.config = config
+        self.groups = config.resnet_groups
+        self.p = {k: v.to(device=self.device, dtype=self.dtype).contiguous() for k, v in params.items()}
+        # the tensor-core conv wants Cin % 64 == 0 and Cout % 8 == 0: zero-pad the two odd layers once
+        self.cin_pad = 64
+        self.p["conv_in.weight"] = _pad_dim(self.p["conv_in.weight"], 3, self.cin_pad)
+        self.cout_pad = 8
+        self.p["conv_out.weight"] = _pad_dim(self.p["conv_out.weight"], 0, self.cout_pad)
+        self.p["conv_out.bias"] = _pad_dim(self.p["conv_out.bias"], 0, self.cout_pad)
+        self._gn_ws = None
+
+    # ------------------------------------------------------------------ building blocks
+    def _gn(self, x, name, silu):
+        B = x.shape[0]
+        n_ws = ops.ctx(self.device.index).lib.dk_groupnorm_ws_floats(B, self.groups)
+        if self._gn_ws is None or self._gn_ws.numel() < n_ws:
+            self._gn_ws = torch.empty(n_ws, dtype=torch.float32, device=self.device)
+        stats = ops.groupnorm_stats(x, self.groups, 1e-5, ws=self._gn_ws)
+        return ops.groupnorm_apply(x, stats, self.p[name + ".weight"], self.p[name + ".bias"], self.groups, silu)
+
+    def _conv(self, x, name, res=None):
+        return ops.conv3x3(x, self.p[name + ".weight"], self.p[name + ".bias"], res=res)
+
+    def _lin(self, x2d, name, res=None):
+        return ops.gemm(x2d, self.p[name + ".weight"], bias=self.p[name + ".bias"], res=res)
+
+    def _resnet(self, x, name):
+        """ResnetBlock2D.__call__ (vae.py:86-101)"""
+        y = self._gn(x, name + ".norm1", True)
+        y = self._conv(y, name + ".conv1")
+        y = self._gn(y, name + ".norm2", True)
+        skip = x
+        if (name + ".conv_shortcut.weight") in self.p:
+            B, H, W, C = x.shape
+            skip = self._lin(x.reshape(B * H * W, C), name + ".conv_shortcut").reshape(B, H, W, -1)
+        return self._conv(y, name + ".conv2", res=skip)
+
+    def _attention(self, x, name):
+        """Attention.__call__ (vae.py:40-57): single head over the H*W positions."""
+        B, H, W, C = x.shape
+        S = H * W
+        y = self._gn(x, name + ".group_norm", False).reshape(B * S, C)
+        q = self._lin(y, name + ".query_proj")
+        k = self._lin(y, name + ".key_proj")
+        v = self._lin(y, name + ".value_proj")
+        scale = 1.0 / math.sqrt(C)
+        o = torch.empty((B * S, C), dtype=self.dtype, device=self.device)
+        scores = torch.empty((S, S), dtype=self.dtype, device=self.device)
+        for b in range(B):
+            sl = slice(b * S, (b + 1) * S)
+            ops.gemm(q[sl], k[sl], out=scores)                       # q k^T
+            ops.softmax_rows(scores, scale)                           # softmax(scale * s)
+            ops.gemm(scores, v[sl], out=o[sl], w_n_major=True)        # P v   (v is [S, C] = [K, N] row-major)
+        out = self._lin(o, name + ".out_proj", res=x.reshape(B * S, C))
+        return out.reshape(B, H, W, C)
+
+    # ------------------------------------------------------------------ forward
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """x (B, H, W, 16) NHWC -> (B, 8H, 8W, 3) NHWC view (channel stride 1, pixel stride 8)."""
+        if x.dim() != 4:
+            raise ValueError(f"VAEDecoder expects NHWC rank-4 input, got rank {x.dim()}")
+        B, H, W, C = x.shape
+        x = x.to(device=self.device, dtype=self.dtype).contiguous()
+        xin = torch.zeros((B, H, W, self.cin_pad), dtype=self.dtype, device=self.device)
+        ops.copy_rows(x, xin, B * H * W, 1, C, self.cin_pad // C, 0, 1, 0)
+        h = self._conv(xin, "conv_in")
+        h = self._resnet(h, "mid_blocks.0")
+        h = self._attention(h, "mid_blocks.1")
+        h = self._resnet(h, "mid_blocks.2")
+        n = len(self.config.block_out_channels)
+        for j in reversed(range(n)):                                  # reversed(self.up_blocks) (vae.py:393)
+            for l in range(self.config.layers_per_block):
+                h = self._resnet(h, f"up_blocks.{j}.resnets.{l}")
+            if f"up_blocks.{j}.upsample.weight" in self.p:
+                h = self._conv(ops.upsample_nearest2x(h), f"up_blocks.{j}.upsample")   # vae.py:146-147
+        h = self._gn(h, "conv_norm_out", True)
+        out = self._conv(h, "conv_out")                               # (B, 8H, 8W, 8) — 3 real channels
+        return out[..., : self.config.out_channels]
