@@ -169,6 +169,7 @@ class DiffusionPipeline:
         self._params, self._vae_params = params, vae_params
         self._load_decoder = load_decoder
         self.check_and_load_models()
+        self._params = self._vae_params = None      # the models hold packed copies; drop the caller's tensors
 
     # ------------------------------------------------------------------ model loading (:90-143)
     def load_mmdit(self, only_modulation_dict=False):
@@ -225,7 +226,11 @@ class DiffusionPipeline:
         seed=None,
         image_path: Optional[str] = None,
         denoise: float = 1.0,
+        *,
+        noise: Optional[torch.Tensor] = None,
     ):
+        """-> (latent NHWC (B, H, W, 16) fp32 on the device, iter_time list).  `noise` (optional, device fp32
+        (B, H, W, 16)) replaces the host-side numpy draw of get_noise for callers whose inputs already live in HBM."""
         if image_path is not None:
             raise NotImplementedError("img2img needs the VAE encoder (SURVEY.md §8 row f3)")
         denoise = 1.0
@@ -249,10 +254,13 @@ class DiffusionPipeline:
                 f"({'[positive | negative] x ' if reps == 2 else ''}{B} image(s)) for cfg_weight={cfg_weight}")
 
         x_T = self.get_empty_latent(H, W)                                   # (1, H, W, 16) host
-        noise = torch.cat([self.get_noise(s, x_T) for s in seeds], dim=0)   # (B, H, W, 16) host fp32
+        if noise is None:
+            noise = torch.cat([self.get_noise(s, x_T) for s in seeds], dim=0)   # (B, H, W, 16) host fp32
+        elif tuple(noise.shape) != (B, H, W, 16):
+            raise DkError(f"noise has shape {tuple(noise.shape)}, expected {(B, H, W, 16)}")
         sigmas = self.get_sigmas(self.sampler, num_steps)
         sigmas = sigmas[int(num_steps * (1 - denoise)):]
-        x = noise.to(self.device, non_blocking=True)
+        x = noise.to(self.device, dtype=torch.float32, non_blocking=True).clone()
         # noise_scaling: sigma0 * noise + (1 - sigma0) * x_T (sampler.py:41-42); x_T is the constant 0.0609
         s0 = float(sigmas[0])
         x = ops.axpb(x.contiguous(), s0, (1.0 - s0) * 0.0609)

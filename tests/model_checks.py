@@ -1,0 +1,197 @@
+"""GPU checks of the assembled models (MMDiT forward, denoise loop, VAE decode, pipeline API) against the fp32 CPU
+oracle on the same synthetic weights and inputs.
+
+Tolerances (stated per SURVEY.md §8c): 16-bit kernels vs the fp32 oracle —
+  MMDiT forward     rel-L2 <= 2e-2 and PSNR >= 35 dB (the reference's own converter gate, tests/torch2coreml/test_mmdit.py:27)
+  final latent      rel-L2 <= 5e-2
+  decoded RGB       PSNR >= 30 dB (4-step FLUX), >= 20 dB (reference e2e floor) for CFG runs
+"""
+import math
+import os
+
+import numpy as np
+import torch
+
+import diffusionkit_b200 as dk
+from diffusionkit_b200 import ops
+from diffusionkit_b200.config import VAEDecoderConfig, tiny_flux_config, tiny_sd3_config
+from diffusionkit_b200.weights import init_params, mmdit_param_specs, vae_decoder_param_specs
+from oracle import sampler_ref as sr
+from oracle.mmdit_ref import MMDiTRef
+from oracle.vae_ref import VAEDecoderRef, decode_latents_to_image, to_uint8
+from tests.oracle_bridge import ref_config
+
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel_l2(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def psnr(ref, got):
+    return sr.compute_psnr(ref.float().cpu().numpy(), got.float().cpu().numpy())
+
+
+def _mmdit_case(cfg, dtype, B, lat, T, seed=7, from_golden=None):
+    p32 = init_params(mmdit_param_specs(cfg), seed=seed, dtype=torch.float32)
+    p16 = {k: v.to(dtype) for k, v in p32.items()}
+    # the oracle sees the same (16-bit-rounded) weights as the GPU
+    ref = MMDiTRef(ref_config(cfg), {k: v.float() for k, v in p16.items()})
+    if from_golden is not None:
+        g = np.load(os.path.join(GOLD, from_golden))
+        latent, text, pooled = [torch.from_numpy(g[k]) for k in ("latent", "text", "pooled")]
+        tval = float(g["timestep"][0])
+    else:
+        gen = torch.Generator().manual_seed(5)
+        latent = torch.randn((B, lat[0], lat[1], 16), generator=gen)
+        text = torch.randn((B, T, cfg.token_level_text_embed_dim), generator=gen)
+        pooled = torch.randn((B, cfg.pooled_text_embed_dim), generator=gen)
+        tval = 752.0
+    latent, text, pooled = [t.to(dtype) for t in (latent, text, pooled)]
+    t = torch.tensor([tval])
+    ref.cache_modulation_params(pooled.float(), t)
+    want = ref(latent.float(), text.float(), t.repeat(latent.shape[0]))
+    m = dk.MMDiT(cfg, {k: v.to(DEV) for k, v in p16.items()})
+    m.cache_modulation_params(pooled.to(DEV), [tval, 0.0])
+    got = m(latent_image_embeddings=latent.to(DEV), token_level_text_embeddings=text.to(DEV).unsqueeze(2),
+            timestep=torch.full((latent.shape[0],), tval))
+    torch.cuda.synchronize()
+    assert got.shape == want.shape and bool(torch.isfinite(got.float()).all())
+    r, ps = rel_l2(got, want), psnr(want, got)
+    assert r <= 2e-2 and ps >= 35.0, f"mmdit rel_l2={r:.3e} psnr={ps:.1f}"
+    # modulation table sanity: every block's rows agree with the oracle
+    return {"rel_l2": r, "psnr": ps}
+
+
+def check_mmdit_flux_tiny():
+    return _mmdit_case(tiny_flux_config(), torch.bfloat16, 2, (8, 12), 16, from_golden="tiny_flux_mmdit.npz")
+
+
+def check_mmdit_sd3_tiny():
+    return _mmdit_case(tiny_sd3_config(), torch.float16, 2, (8, 8), 24, from_golden="tiny_sd3_mmdit.npz")
+
+
+def check_mmdit_flux_ragged():
+    """sequence lengths that are not tile multiples: N = 14*18 = 252 image tokens + 77 text tokens, head dim 128"""
+    return _mmdit_case(tiny_flux_config(hidden=256, heads=2, depth_mm=2, depth_uni=3), torch.bfloat16, 3, (28, 36), 77)
+
+
+def check_mmdit_sd3_d64_long():
+    return _mmdit_case(tiny_sd3_config(hidden=192, heads=3, depth_mm=3), torch.float16, 2, (32, 40), 154)
+
+
+def _vae_case(dtype, B, lat, tol_psnr):
+    vp32 = init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=8, dtype=torch.float32)
+    vp16 = {k: v.to(dtype) for k, v in vp32.items()}
+    gen = torch.Generator().manual_seed(4)
+    z = torch.randn((B, lat[0], lat[1], 16), generator=gen).to(dtype)
+    want = decode_latents_to_image(VAEDecoderRef({k: v.float() for k, v in vp16.items()}), z.float())
+    dec = dk.VAEDecoder({k: v.to(DEV) for k, v in vp16.items()})
+    raw = dec(z.to(DEV))
+    Bo, Ho, Wo, _ = raw.shape
+    padded = raw.as_strided((Bo, Ho, Wo, raw.stride(2)), (raw.stride(0), raw.stride(1), raw.stride(2), 1))
+    f, u8 = ops.image_post(padded)
+    torch.cuda.synchronize()
+    assert f.shape == want.shape
+    ps = psnr(want, f)
+    du8 = (u8.cpu().int() - to_uint8(want).int()).abs()
+    assert ps >= tol_psnr, f"vae psnr {ps:.1f}"
+    return {"psnr": ps, "u8_max_diff": int(du8.max()), "u8_mean_diff": float(du8.float().mean())}
+
+
+def check_vae_decode_tiny():
+    return _vae_case(torch.bfloat16, 1, (8, 8), 30.0)
+
+
+def check_vae_decode_batch_fp16():
+    return _vae_case(torch.float16, 2, (8, 12), 40.0)
+
+
+def _pipeline_case(kind):
+    """Full denoise loop + decode through the public API vs the oracle loop (same seeds, steps, shift, cfg)."""
+    vp32 = init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=8, dtype=torch.float32)
+    if kind == "flux":
+        cfg, dtype, steps, cfgw, shift, T, fmt = tiny_flux_config(), torch.bfloat16, 4, 0.0, 1.0, 16, "flux"
+    else:
+        cfg, dtype, steps, cfgw, shift, T, fmt = tiny_sd3_config(), torch.float16, 6, 5.0, 3.0, 24, "sd3"
+    p32 = init_params(mmdit_param_specs(cfg), seed=7, dtype=torch.float32)
+    p16 = {k: v.to(dtype) for k, v in p32.items()}
+    vp16 = {k: v.to(dtype) for k, v in vp32.items()}
+    Pipe = dk.FluxPipeline if kind == "flux" else dk.DiffusionPipeline
+    mv = "argmaxinc/mlx-FLUX.1-schnell" if kind == "flux" else "argmaxinc/mlx-stable-diffusion-3-medium"
+    pipe = Pipe(w16=True, a16=True, shift=shift, model_version=mv, mmdit_config=cfg,
+                params={k: v.to(DEV) for k, v in p16.items()}, vae_params={k: v.to(DEV) for k, v in vp16.items()})
+    seeds = [11, 12]
+    n = len(seeds)
+    cond, pooled = pipe.synthetic_text_embeddings(n_images=n, text_len=T)
+    H, W = 8, 12
+    latent, iter_time = pipe.denoise_latents(cond, pooled, num_steps=steps, cfg_weight=cfgw, latent_size=(H, W),
+                                             seed=seeds)
+    assert latent.shape == (n, H, W, 16) and latent.dtype == torch.float32 and len(iter_time) == steps
+    # oracle loop, one image at a time exactly like the reference (batch 1, CFG doubles it)
+    sampler = sr.FluxSamplerRef(shift) if kind == "flux" else sr.ModelSamplingDiscreteFlowRef(shift)
+    sig = sr.get_sigmas(sampler, steps)
+    outs = []
+    reps = 2 if cfgw > 0 else 1
+    for i, s in enumerate(seeds):
+        ref = MMDiTRef(ref_config(cfg), {k: v.float() for k, v in p16.items()})
+        idx = [i + k * n for k in range(reps)]
+        c_i, p_i = cond[idx].float(), pooled[idx].float()
+        x0 = sampler.noise_scaling(float(sig[0]), sr.get_noise(s, H, W), sr.get_empty_latent(H, W))
+        x = sr.sample_euler(lambda xin, c, t: ref(xin, c, t), ref.cache_modulation_params, x0, sig, c_i, p_i, cfgw, dtype)
+        outs.append(sr.process_out(x, fmt))
+    want = torch.cat(outs)
+    r = rel_l2(latent, want)
+    assert r <= 5e-2, f"{kind} final latent rel_l2 {r:.3e}"
+    img_want = decode_latents_to_image(VAEDecoderRef({k: v.float() for k, v in vp16.items()}), want.to(dtype).float())
+    img_got = pipe.decode_latents_to_image(latent)
+    ps = psnr(img_want, img_got)
+    assert ps >= (30.0 if kind == "flux" else 20.0), f"{kind} decoded RGB psnr {ps:.1f}"
+    # public generate_image: returns (PIL image, log) for a scalar seed, list for a list of seeds
+    c1, p1 = cond[[0] + ([n] if reps == 2 else [])], pooled[[0] + ([n] if reps == 2 else [])]
+    image, log = pipe.generate_image("", num_steps=steps, cfg_weight=cfgw, latent_size=(H, W), seed=seeds[0],
+                                     verbose=False, conditioning=c1, pooled_conditioning=p1)
+    assert image.size == (W * 8, H * 8)
+    for k in ("text_encoding", "denoising", "decoding", "peak_memory", "total_time"):
+        assert k in log
+    assert len(log["denoising"]["iter_time"]) == steps
+    u8 = np.asarray(image)
+    want_u8 = to_uint8(img_want[0]).numpy()
+    return {"latent_rel_l2": r, "rgb_psnr": ps, "u8_mean_abs_diff": float(np.abs(u8.astype(int) - want_u8.astype(int)).mean())}
+
+
+def check_pipeline_flux_tiny():
+    return _pipeline_case("flux")
+
+
+def check_pipeline_sd3_cfg_tiny():
+    return _pipeline_case("sd3")
+
+
+def check_pipeline_errors():
+    cfg = tiny_flux_config()
+    pipe = dk.FluxPipeline(w16=True, a16=True, mmdit_config=cfg, load_decoder=False)
+    cond, pooled = pipe.synthetic_text_embeddings(text_len=8)
+    try:
+        pipe.generate_image("x", latent_size=(7, 8), conditioning=cond, pooled_conditioning=pooled)
+        raise RuntimeError("odd latent size accepted")
+    except AssertionError:
+        pass
+    try:
+        pipe.encode_text("a prompt")
+        raise RuntimeError("encode_text should be NotImplemented")
+    except NotImplementedError:
+        pass
+    try:
+        pipe.mmdit(torch.zeros(1, 8, 16, dtype=torch.bfloat16, device=DEV), cond.to(DEV), 0.0)
+        raise RuntimeError("rank-3 latent accepted")
+    except ValueError:
+        pass
+    return {}
+
+
+ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
+              check_vae_decode_tiny, check_vae_decode_batch_fp16, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
+              check_pipeline_errors]

@@ -14,8 +14,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
         import kernel_checks as kc
+        import model_checks as mc
 
-        fn = getattr(kc, sys.argv[2])
+        fn = getattr(kc, sys.argv[2], None) or getattr(mc, sys.argv[2])
         t0 = time.time()
         res = fn()
         import torch
@@ -24,8 +25,9 @@ def main():
         print("RESULT " + json.dumps({"ok": True, "res": res, "sec": round(time.time() - t0, 2)}))
         return
     import kernel_checks as kc
+    import model_checks as mc
 
-    names = [c.__name__ for c in kc.ALL_CHECKS]
+    names = [c.__name__ for c in kc.ALL_CHECKS + mc.ALL_CHECKS]
     filt = sys.argv[1:]
     if filt:
         names = [n for n in names if any(f in n for f in filt)]
@@ -35,7 +37,7 @@ def main():
     env = dict(os.environ, DK_DUMP_DIR=os.path.join(out_dir, "dumps"))
     for n in names:
         try:
-            p = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=240,
+            p = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=400,
                                env=env)
             line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
             if line:
