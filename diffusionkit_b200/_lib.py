@@ -37,6 +37,8 @@ class GemmArgs(C.Structure):
         ("out_batch_rows", i32), ("out_row_off", i32),
         ("res_batch_rows", i32), ("res_row_off", i32),
         ("act", i32), ("w_n_major", i32),
+        ("qk_q_weight", vp), ("qk_k_weight", vp), ("qk_rope", vp),
+        ("qk_heads", i32), ("qk_head_dim", i32), ("qk_eps", f32),
     ]
 
 

@@ -11,8 +11,10 @@
 //   warp 1 : MMA issuer       — one thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator;
 //                               tcgen05.commit releases smem stages / publishes the accumulator.
 //   warp 2 : TMEM allocator   — 2*BN columns: two accumulators, so tile i+1's mainloop overlaps tile i's epilogue.
-//   warps 4-7 : epilogue      — tcgen05.ld (lane = row), fused bias / GELU-erf / adaLN gate / residual,
-//                               128-bit stores straight to the destination row (row remap = joint-sequence scatter).
+//   warps 4-11: epilogue      — tcgen05.ld (lane = row; two warps per TMEM lane quarter, each owning half of the
+//                               tile's columns), fused bias / GELU-erf / adaLN gate / residual, or QK-RMSNorm + RoPE
+//                               on the q/k thirds of a packed QKV projection; 128-bit stores straight to the
+//                               destination row (row remap = joint-sequence scatter).
 #include "common.cuh"
 #include "host.h"
 
@@ -21,7 +23,7 @@ namespace dk {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue (2 per TMEM lane quarter)
 
 struct GemmShape {
   int M, N, K;
@@ -40,6 +42,12 @@ struct GemmEpi {
   int out_batch_rows, out_row_off;
   int res_batch_rows, res_row_off;
   int act;
+  // fused QK-RMSNorm + RoPE on the q and k thirds of a packed QKV projection (columns [0, 2*qk_h)); qk_d == 0 disables
+  const void* qk_qw;   // [d] RMSNorm weight of q (or NULL: no norm)
+  const void* qk_kw;   // [d]
+  const float* qk_rope;  // [S, d/2, 2] (cos, sin) or NULL
+  int qk_h, qk_d;
+  float qk_eps;
 };
 
 struct ConvGeom {
@@ -97,7 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], 256);
     }
     fence_barrier_init();
   }
@@ -199,8 +207,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (128 threads, lane = tile row)
-    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. 32*quarter+31 are accessible to this warp
+    // ------------------------------------------------------------------ epilogue (256 threads, lane = tile row)
+    const int quarter = warp & 3;          // TMEM lanes 32*quarter .. 32*quarter+31 are accessible to this warp
+    const int half = (warp - 4) >> 2;      // which half of the tile's columns this warp drains
+    constexpr int NCH = BN / 64;           // 32-column chunks per warp
     const int r_in_tile = quarter * 32 + lane;
     const T* bias = reinterpret_cast<const T*>(e.bias);
     const T* gate = reinterpret_cast<const T*>(e.gate);
@@ -216,12 +226,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // destination rows
       bool row_ok;
       long long orow, rrow;
-      int batch;
+      int batch, pos = 0;
       if (MODE == 0) {
         const int m = m_blk * BM + r_in_tile;
         row_ok = m < s.M;
         batch = m / e.rpb;
         const int in_b = m - batch * e.rpb;
+        pos = e.out_row_off + in_b;  // position in the joint sequence (RoPE)
         orow = static_cast<long long>(batch) * e.out_batch_rows + e.out_row_off + in_b;
         rrow = static_cast<long long>(batch) * e.res_batch_rows + e.res_row_off + in_b;
       } else {
@@ -238,19 +249,124 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
+      const int n_half0 = n_blk * BN + half * (BN / 2);
+
+      auto release_acc = [&]() {
+        // accumulator columns of this warp fully drained into registers: hand the TMEM buffer back to the MMA warp
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      };
+
+      if (MODE == 0 && e.qk_d != 0 && n_half0 < 2 * e.qk_h) {
+        // ---- q / k columns of a packed QKV projection: RMSNorm over each head (two passes over TMEM), then RoPE.
+        //      reference: q = Linear(m) (16-bit) -> nn.RMSNorm (fp32 accumulate, 16-bit out) -> RoPE in fp32
+        //      (mlx/mmdit.py:471-488, 754-764, 934-942)
+        const int d = e.qk_d;
+        const int cph = d >> 5;  // chunks per head
+        const T* nw = reinterpret_cast<const T*>(n_half0 < e.qk_h ? e.qk_qw : e.qk_kw);
+#pragma unroll 1
+        for (int hc = 0; hc < NCH; hc += cph) {
+          float ss = 0.f;
+          if (nw != nullptr) {
+#pragma unroll 1
+            for (int c = 0; c < cph; ++c) {
+              uint32_t r[32];
+              tmem_ld_32x32(t_row + (hc + c) * 32, r);
+              tmem_ld_wait();
+              const int n0 = n_half0 + (hc + c) * 32;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float bv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bv[i] = 0.f;
+                if (bias != nullptr) {
+                  const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n0 + j * 8);
+                  const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 f = H16::unpack(bw[i]);
+                    bv[2 * i] = f.x;
+                    bv[2 * i + 1] = f.y;
+                  }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float v = H16::to_f(H16::from_f(__uint_as_float(r[j * 8 + i]) + bv[i]));
+                  ss += v * v;
+                }
+              }
+            }
+          }
+          const float rstd = rsqrtf(ss / d + e.qk_eps);
+          const int head_col0 = (n_half0 + hc * 32) % d;  // 0: tiles are head aligned
+#pragma unroll 1
+          for (int c = 0; c < cph; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(t_row + (hc + c) * 32, r);
+            tmem_ld_wait();
+            if (hc + c == NCH - 1) release_acc();
+            if (!row_ok) continue;
+            const int n0 = n_half0 + (hc + c) * 32;
+            const int dcol0 = head_col0 + c * 32;  // column inside the head
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = n0 + j * 8;
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+              if (bias != nullptr) {
+                const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n);
+                const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = H16::unpack(bw[i]);
+                  v[2 * i] += f.x;
+                  v[2 * i + 1] += f.y;
+                }
+              }
+              if (nw != nullptr) {
+                const uint4 w4 = *reinterpret_cast<const uint4*>(nw + dcol0 + j * 8);
+                const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = H16::unpack(ww[i]);
+                  v[2 * i] = H16::to_f(H16::from_f(H16::to_f(H16::from_f(v[2 * i])) * rstd * f.x));
+                  v[2 * i + 1] = H16::to_f(H16::from_f(H16::to_f(H16::from_f(v[2 * i + 1])) * rstd * f.y));
+                }
+              }
+              if (e.qk_rope != nullptr) {
+                const float4* rp = reinterpret_cast<const float4*>(
+                    e.qk_rope + (static_cast<long long>(pos) * (d >> 1) + ((dcol0 + j * 8) >> 1)) * 2);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  const float4 cs = rp[i];  // (cos0, sin0, cos1, sin1)
+                  const float a0 = v[4 * i], a1 = v[4 * i + 1], b0 = v[4 * i + 2], b1 = v[4 * i + 3];
+                  v[4 * i] = a0 * cs.x - a1 * cs.y;
+                  v[4 * i + 1] = a0 * cs.y + a1 * cs.x;
+                  v[4 * i + 2] = b0 * cs.z - b1 * cs.w;
+                  v[4 * i + 3] = b0 * cs.w + b1 * cs.z;
+                }
+              }
+              uint4 o;
+              o.x = H16::pack(v[0], v[1]);
+              o.y = H16::pack(v[2], v[3]);
+              o.z = H16::pack(v[4], v[5]);
+              o.w = H16::pack(v[6], v[7]);
+              *reinterpret_cast<uint4*>(out + orow * e.ldc + n) = o;
+            }
+          }
+        }
+        continue;
+      }
 
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = 0; chunk < NCH; ++chunk) {
         uint32_t r[32];
         tmem_ld_32x32(t_row + chunk * 32, r);
         tmem_ld_wait();
-        if (chunk == BN / 32 - 1) {
-          // accumulator fully drained into registers: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[acc]);
-        }
-        const int n0 = n_blk * BN + chunk * 32;
+        if (chunk == NCH - 1) release_acc();
+        const int n0 = n_half0 + chunk * 32;
         if (!row_ok) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -379,7 +495,7 @@ extern "C" int dk_gemm(dk_ctx* ctx, const dk_gemm_args* a, void* stream_) {
   s.K = a->K;
   s.num_m = dk_ceil_div(a->M, BM);
   s.num_k = dk_ceil_div(a->K, BK);
-  const int bn = a->w_n_major ? 128 : pick_bn(ctx, s.num_m, a->N);
+  const int bn = a->w_n_major ? 128 : (a->qk_head_dim != 0 ? 256 : pick_bn(ctx, s.num_m, a->N));
   s.num_n = dk_ceil_div(a->N, bn);
 
   GemmEpi e;
@@ -396,6 +512,19 @@ extern "C" int dk_gemm(dk_ctx* ctx, const dk_gemm_args* a, void* stream_) {
   e.res_batch_rows = a->rows_per_batch > 0 ? a->res_batch_rows : a->M;
   e.res_row_off = a->res_row_off;
   e.act = a->act;
+  e.qk_qw = a->qk_q_weight;
+  e.qk_kw = a->qk_k_weight;
+  e.qk_rope = a->qk_rope;
+  e.qk_d = a->qk_head_dim;
+  e.qk_h = a->qk_heads * a->qk_head_dim;
+  e.qk_eps = a->qk_eps;
+  if (e.qk_d != 0) {
+    DK_REQUIRE(e.qk_d == 64 || e.qk_d == 128, "dk_gemm: fused QK norm/RoPE supports head dims 64 and 128 (got %d)", e.qk_d);
+    DK_REQUIRE(a->N == 3 * e.qk_h && e.qk_h % 128 == 0, "dk_gemm: fused QK epilogue needs N == 3*heads*d, heads*d %% 128 == 0");
+    DK_REQUIRE(!a->w_n_major && a->act == DK_ACT_NONE && a->gate == nullptr && a->res == nullptr,
+               "dk_gemm: fused QK epilogue excludes act/gate/residual");
+    DK_REQUIRE(a->qk_rope == nullptr || (reinterpret_cast<uintptr_t>(a->qk_rope) & 15u) == 0, "dk_gemm: rope table alignment");
+  }
   ConvGeom g = {};
 
   CUtensorMap tmA, tmB;

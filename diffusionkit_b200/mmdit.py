@@ -6,8 +6,9 @@ Host-side mirror of the reference module (python/src/diffusionkit/mlx/mmdit.py:2
 through the C ABI (ops.py -> libdkb200.so); torch tensors are only the HBM containers.
 
 B200 layout decisions (vs. the reference's per-module MLX graph):
-  * q/k/v projections of a stream are ONE GEMM (packed [3h, h] weight; k has no bias — quirk Q3) whose epilogue scatters
-    rows straight into the joint [text|image] (FLUX) / [image|text] (SD3) sequence buffer — no concat kernels.
+  * q/k/v projections of a stream are ONE GEMM (packed [3h, h] weight; k has no bias — quirk Q3) whose epilogue applies
+    the per-head QK-RMSNorm and RoPE (FLUX) and scatters rows straight into the joint [text|image] (FLUX) /
+    [image|text] (SD3) sequence buffer — no norm / rope / concat kernels.
   * adaLN gate * (.) + residual is fused into the o_proj / fc2 GEMM epilogues (in place on the residual stream);
     bias + exact-erf GELU into fc1's.
   * FLUX single-stream blocks: attention output and GELU(fc1) land in one [B*S, 5h] buffer and
@@ -241,11 +242,17 @@ class MMDiT:
         return self._rope
 
     # ------------------------------------------------------------------------------------------ forward
-    def _attn_stream_pre(self, s: _Stream, x, m, rows_per_batch, S, row_off, qkv):
+    def _qk_fused(self, s: _Stream, rope):
+        """epilogue spec for the packed QKV GEMM: per-head QK-RMSNorm (+ RoPE) fused in (None: nothing to fuse)"""
+        if s.q_norm is None and rope is None:
+            return None
+        return (self.heads, self.d, s.q_norm, s.k_norm, rope, 1e-6)
+
+    def _attn_stream_pre(self, s: _Stream, x, m, rows_per_batch, S, row_off, qkv, rope):
         ops.ln_modulate(x, self._mod(s.mod_off, 0), self._mod(s.mod_off, 1), rows_per_batch,
                         self.config.layer_norm_eps, out=m)
         ops.gemm(m, s.w_qkv, out=qkv, bias=s.b_qkv, rows_per_batch=rows_per_batch, out_batch_rows=S,
-                 out_row_off=row_off)
+                 out_row_off=row_off, qk=self._qk_fused(s, rope))
 
     def _stream_post(self, s: _Stream, x, o, m, hid, rows_per_batch):
         """x += gate1 * o_proj(o); x += gate2 * fc2(gelu(fc1(LN(x)(1+scale2)+shift2)))  (mmdit.py:521-548)"""
@@ -313,11 +320,8 @@ class MMDiT:
             off_img, off_txt, split = 0, N, N
 
         for (si, st) in self.double:
-            self._attn_stream_pre(si, img, ws["m_img"], N, S, off_img, qkv)
-            self._attn_stream_pre(st, txt, ws["m_txt"], T, S, off_txt, qkv)
-            if c.use_qk_norm or rope is not None:
-                first, second = (st, si) if self.is_flux else (si, st)
-                ops.qk_norm_rope(qkv, S, heads, d, split, first.q_norm, first.k_norm, second.q_norm, second.k_norm, rope)
+            self._attn_stream_pre(si, img, ws["m_img"], N, S, off_img, qkv, rope)
+            self._attn_stream_pre(st, txt, ws["m_txt"], T, S, off_txt, qkv, rope)
             if self.is_flux:
                 ops.attention(qkv, B, S, heads, d, ws["o_txt"], split=split, out1=ws["o_img"])
             else:
@@ -332,8 +336,8 @@ class MMDiT:
             ops.copy_rows(img, u, B, N, h, S, T, N, 0)
             for s in self.single:                                                      # mmdit.py:693-751
                 ops.ln_modulate(u, self._mod(s.mod_off, 0), self._mod(s.mod_off, 1), S, c.layer_norm_eps, out=m_u)
-                ops.gemm(m_u, s.w_qkv, out=qkv, bias=s.b_qkv)
-                ops.qk_norm_rope(qkv, S, heads, d, S, s.q_norm, s.k_norm, None, None, rope)
+                ops.gemm(m_u, s.w_qkv, out=qkv, bias=s.b_qkv, rows_per_batch=S, out_batch_rows=S,
+                         qk=self._qk_fused(s, rope))
                 ops.attention(qkv, B, S, heads, d, cat[:, :h])
                 ops.gemm(m_u, s.w_fc1, out=cat[:, h:], bias=s.b_fc1, act=ACT_GELU_ERF)
                 ops.gemm(cat, s.w_out, out=u, bias=s.b_o, gate=self._mod(s.mod_off, 2), res=u, rows_per_batch=S,

@@ -53,6 +53,7 @@ def gemm(
     res_row_off: int = 0,
     w_n_major: bool = False,
     N: Optional[int] = None,
+    qk: Optional[tuple] = None,
 ) -> torch.Tensor:
     """out = res + gate * act(A @ W.T + bias)   (see include/dkb200.h, dk_gemm).
 
@@ -94,6 +95,11 @@ def gemm(
     a.res_row_off = res_row_off
     a.act = act
     a.w_n_major = 1 if w_n_major else 0
+    if qk is not None:
+        # (heads, head_dim, q_norm_weight | None, k_norm_weight | None, rope table | None, eps)
+        heads, hd, qw, kw, rope, eps = qk
+        a.qk_heads, a.qk_head_dim, a.qk_eps = heads, hd, eps
+        a.qk_q_weight, a.qk_k_weight, a.qk_rope = ptr(qw), ptr(kw), ptr(rope)
     c = ctx(A.device.index)
     c.check(c.lib.dk_gemm(c.handle, C.byref(a), c.stream))
     return out

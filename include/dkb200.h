@@ -73,6 +73,15 @@ typedef struct dk_gemm_args {
   int res_batch_rows, res_row_off;
   int act;       /* DK_ACT_* applied to (acc + bias) */
   int w_n_major; /* 1: W is [K, N] row-major (exercises the MN-major operand path used for V) */
+  /* fused epilogue for a packed [q | k | v] projection (N = 3 * qk_heads * qk_head_dim), qk_head_dim = 0 disables:
+   * per head of the q and k thirds  x = RMSNorm(x; weight, qk_eps)  (mmdit.py:754-764; NULL weight = no norm)
+   * then RoPE with table qk_rope[pos][pair] = (cos, sin), pos = out_row_off + m % rows_per_batch (mmdit.py:934-942;
+   * NULL = no RoPE).  Replaces a separate dk_qk_norm_rope pass over the QKV buffer. */
+  const void* qk_q_weight;
+  const void* qk_k_weight;
+  const float* qk_rope;
+  int qk_heads, qk_head_dim;
+  float qk_eps;
 } dk_gemm_args;
 int dk_gemm(dk_ctx* ctx, const dk_gemm_args* args, void* stream);
 

@@ -224,6 +224,14 @@ def check_attention_d64():
     return out
 
 
+def check_attention_v1_kernel():
+    """the single-Q-tile kernel with P staged through shared memory (DK_ATTENTION_V1=1) stays correct"""
+    os.environ["DK_ATTENTION_V1"] = "1"
+    _setup()
+    return {"d128": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att_v1_d128"),
+            "d64": _attention_case(1, 1178, 2, 64, torch.float16, split=1024, name="att_v1_d64")}
+
+
 def check_attention_large_scores():
     """rows whose running max keeps growing: exercises the lazy O rescale path."""
     _setup()
@@ -290,6 +298,50 @@ def check_qk_norm_rope():
             ref[:, which * h:(which + 1) * h] = t.reshape(B * S, h)
         got = ops.qk_norm_rope(qkv.clone(), S, heads, d, split, ws[0], ws[1], ws[2], ws[3], rope)
         out[f"d{d}_{use_norm}_{use_rope}"] = _assert_close(f"qknr_{d}", got, ref, 4e-3)
+    return out
+
+
+def check_gemm_fused_qk_norm_rope():
+    """packed QKV projection with the QK-RMSNorm + RoPE epilogue == plain GEMM followed by dk_qk_norm_rope,
+    and == an fp32 torch evaluation"""
+    _setup()
+    out = {}
+    for (Bt, Ss, off, S, heads, d, dt, use_norm, use_rope) in [(2, 100, 28, 128, 2, 128, torch.bfloat16, True, True),
+                                                               (1, 300, 0, 300, 4, 64, torch.float16, True, True),
+                                                               (2, 77, 5, 90, 2, 128, torch.bfloat16, False, True)]:
+        h = heads * d
+        K = 192
+        A = _rand((Bt * Ss, K), dt)
+        W = _rand((3 * h, K), dt, 1 / math.sqrt(K))
+        bias = _rand((3 * h,), dt, 0.3)
+        qw = (_rand((d,), dt, 0.1) + 1.0) if use_norm else None
+        kw = (_rand((d,), dt, 0.1) + 1.0) if use_norm else None
+        rope = _rope_table(S, d, DEV) if use_rope else None
+        fused = torch.zeros((Bt * S, 3 * h), dtype=dt, device=DEV)
+        ops.gemm(A, W, out=fused, bias=bias, rows_per_batch=Ss, out_batch_rows=S, out_row_off=off,
+                 qk=(heads, d, qw, kw, rope, 1e-6))
+        plain = torch.zeros((Bt * S, 3 * h), dtype=dt, device=DEV)
+        ops.gemm(A, W, out=plain, bias=bias, rows_per_batch=Ss, out_batch_rows=S, out_row_off=off)
+        ops.qk_norm_rope(plain, S, heads, d, S, qw, kw, None, None, rope)
+        rows = torch.cat([torch.arange(b * S + off, b * S + off + Ss) for b in range(Bt)]).to(DEV)
+        out[f"vs_unfused_d{d}_{use_norm}"] = _assert_close(f"fusedqk_{d}", fused[rows], plain[rows], 3e-3)
+        other = torch.ones(Bt * S, dtype=torch.bool, device=DEV)
+        other[rows] = False
+        assert float(fused[other].float().abs().max()) == 0.0, "rows outside the scatter window were written"
+        # fp32 reference
+        y = (A.float() @ W.float().t() + bias.float())
+        pos = (torch.arange(Bt * Ss, device=DEV) % Ss) + off
+        ref = y.clone()
+        for which, w in enumerate([qw, kw]):
+            t = y[:, which * h:(which + 1) * h].reshape(-1, heads, d)
+            if use_norm:
+                t = t * torch.rsqrt((t * t).mean(-1, keepdim=True) + 1e-6) * w.float()
+            if use_rope:
+                c, sn = rope[pos][:, None, :, 0], rope[pos][:, None, :, 1]
+                x0, x1 = t[..., 0::2], t[..., 1::2]
+                t = torch.stack([x0 * c - x1 * sn, x0 * sn + x1 * c], dim=-1).reshape(-1, heads, d)
+            ref[:, which * h:(which + 1) * h] = t.reshape(-1, h)
+        out[f"vs_fp32_d{d}_{use_norm}"] = _assert_close(f"fusedqk_ref_{d}", fused[rows], ref, 6e-3)
     return out
 
 
@@ -396,8 +448,9 @@ def check_softmax_image_post():
 
 ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
-    check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_conv3x3,
+    check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope, check_conv3x3,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
+    check_attention_v1_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post,
 ]
