@@ -327,7 +327,8 @@ def check_gemm_fused_qk_norm_rope():
         out[f"vs_unfused_d{d}_{use_norm}"] = _assert_close(f"fusedqk_{d}", fused[rows], plain[rows], 3e-3)
         other = torch.ones(Bt * S, dtype=torch.bool, device=DEV)
         other[rows] = False
-        assert float(fused[other].float().abs().max()) == 0.0, "rows outside the scatter window were written"
+        if bool(other.any()):
+            assert float(fused[other].float().abs().max()) == 0.0, "rows outside the scatter window were written"
         # fp32 reference
         y = (A.float() @ W.float().t() + bias.float())
         pos = (torch.arange(Bt * Ss, device=DEV) % Ss) + off
