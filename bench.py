@@ -223,11 +223,19 @@ def run_ours(args):
     x_T = pipe.get_empty_latent(lat, lat)
     noise_dev = torch.cat([pipe.get_noise(s, x_T) for s in seeds]).to(dev)
 
+    split = {"denoise": 0.0, "decode": 0.0}
+
     def step_device():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
         latent, _ = pipe.denoise_latents(cond_dev, pooled_dev, num_steps=steps, cfg_weight=cfgw,
                                          latent_size=(lat, lat), seed=seeds, noise=noise_dev)
+        ev[1].record()
         lat16 = ops.cast_to_16(latent, pipe.activation_dtype)
-        return pipe._decode(lat16, want_u8=True)
+        out = pipe._decode(lat16, want_u8=True)
+        ev[2].record()
+        split["ev"] = ev
+        return out
 
     def step_e2e():
         imgs, log = pipe.generate_image("", num_steps=steps, cfg_weight=cfgw, latent_size=(lat, lat), seed=seeds,
@@ -257,6 +265,8 @@ def run_ours(args):
     barrier()
     launches = ops.launch_count() - launches0
     clk = clocks.stop()
+    split["denoise"] = split["ev"][0].elapsed_time(split["ev"][1])
+    split["decode"] = split["ev"][1].elapsed_time(split["ev"][2])
     t_dev = dkd.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
 
     # ---- timed region 2: end to end through the public API with host inputs / outputs
@@ -327,6 +337,7 @@ def run_ours(args):
                      "peak_source": f"{peaks['source']} bf16 burst (sustained {peaks['bf16_tflops_sustained']})",
                      "launches_timed": n_gemm, "gemm_seconds_of_one_step": t_gemm},
         "mmdit_tensor_frac_sustained": mmdit_frac,
+        "last_step_ms": {"denoise": split["denoise"], "decode": split["decode"]},
         "denoise_tflops_per_image": flops_img / 1e12,
         "weights_init_broadcast_s": t_weights,
     }

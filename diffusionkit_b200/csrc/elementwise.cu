@@ -337,19 +337,28 @@ __global__ void cast_16_to_f32_kernel(const T* __restrict__ x, float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm (VAE).  stats: two-stage, deterministic (no atomics):
-//   stage 1: grid (GN_CHUNKS, B); each block reduces its pixel slab to per-group (sum, sumsq) partials
-//   stage 2: one warp per (b, g) folds the partials in double and writes (mean, rstd)
+// GroupNorm (VAE).  stats: two-stage, deterministic (no atomics across blocks):
+//   stage 1: grid (chunks, B); each block reduces its pixel slab to per-group (sum, sumsq) partials
+//   stage 2: one thread per (b, g) folds the partials in double and writes (mean, rstd)
+// apply: grid (blocks, B); a thread keeps its 8 channels' (scale, shift) in registers and streams pixels.
 // ------------------------------------------------------------------------------------------------
-constexpr int GN_CHUNKS = 64;
+constexpr int GN_MAX_CHUNKS = 1024;
 constexpr int GN_THREADS = 256;
+
+static inline int gn_chunks(int HW) {
+  // >= 64 pixels per block, at most GN_MAX_CHUNKS blocks per image
+  int c = (HW + 63) / 64;
+  if (c > GN_MAX_CHUNKS) c = GN_MAX_CHUNKS;
+  if (c < 1) c = 1;
+  return c;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
-groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C, int G) {
+groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int chunks) {
   extern __shared__ float sm[];  // [2*C]
   const int b = blockIdx.y, chunk = blockIdx.x;
-  const int per = (HW + GN_CHUNKS - 1) / GN_CHUNKS;
+  const int per = (HW + chunks - 1) / chunks;
   const int p0 = chunk * per;
   const int p1 = min(HW, p0 + per);
   const int vec_per_pix = C / 8;
@@ -360,9 +369,22 @@ groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, i
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
   if (my_pix < pix_per_iter) {
-    for (int p = p0 + my_pix; p < p1; p += pix_per_iter) {
+    const T* base = x + static_cast<long long>(b) * HW * C + my_vec * 8;
+    int p = p0 + my_pix;
+    // two independent loads in flight per thread
+    for (; p + pix_per_iter < p1; p += 2 * pix_per_iter) {
+      float v0[8], v1[8];
+      load8(base + static_cast<long long>(p) * C, v0);
+      load8(base + static_cast<long long>(p + pix_per_iter) * C, v1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += v0[j] + v1[j];
+        q[j] += v0[j] * v0[j] + v1[j] * v1[j];
+      }
+    }
+    for (; p < p1; p += pix_per_iter) {
       float v[8];
-      load8(x + (static_cast<long long>(b) * HW + p) * C + my_vec * 8, v);
+      load8(base + static_cast<long long>(p) * C, v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j] += v[j];
@@ -387,19 +409,19 @@ groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, i
       ts += sm[g * cpg + c];
       tq += sm[C + g * cpg + c];
     }
-    float* dst = partial + ((static_cast<long long>(b) * GN_CHUNKS + chunk) * G + g) * 2;
+    float* dst = partial + ((static_cast<long long>(b) * chunks + chunk) * G + g) * 2;
     dst[0] = ts;
     dst[1] = tq;
   }
 }
 __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int B, int G,
-                                          double count, float eps) {
+                                          int chunks, double count, float eps) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * G) return;
   const int b = idx / G, g = idx % G;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < GN_CHUNKS; ++c) {
-    const float* p = partial + ((static_cast<long long>(b) * GN_CHUNKS + c) * G + g) * 2;
+  for (int c = 0; c < chunks; ++c) {
+    const float* p = partial + ((static_cast<long long>(b) * chunks + c) * G + g) * 2;
     s += p[0];
     q += p[1];
   }
@@ -410,29 +432,40 @@ __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, flo
   stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
 }
 template <typename T>
-__global__ void groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
-                                       const T* __restrict__ gamma, const T* __restrict__ beta, int B, int HW, int C,
-                                       int G, int silu) {
-  const long long nvec = static_cast<long long>(B) * HW * C / 8;
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ stats,
+                       const T* __restrict__ gamma, const T* __restrict__ beta, int HW, int C, int G, int silu) {
+  const int b = blockIdx.y;
+  const int vec_per_pix = C / 8;
+  const int pix_per_iter = GN_THREADS / vec_per_pix;
+  const int my_vec = threadIdx.x % vec_per_pix;
+  const int my_pix = threadIdx.x / vec_per_pix;
+  if (my_pix >= pix_per_iter) return;
   const int cpg = C / G;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long e = i * 8;
-    const int c0 = static_cast<int>(e % C);
-    const int b = static_cast<int>(e / (static_cast<long long>(HW) * C));
-    float v[8], ga[8], be[8];
-    load8(x + e, v);
-    load8(gamma + c0, ga);
-    load8(beta + c0, be);
+  float sc[8], sh[8];
+  {
+    float ga[8], be[8];
+    load8(gamma + my_vec * 8, ga);
+    load8(beta + my_vec * 8, be);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / cpg;
+      const int g = (my_vec * 8 + j) / cpg;
       const float mean = stats[(b * G + g) * 2], rstd = stats[(b * G + g) * 2 + 1];
-      float o = (v[j] - mean) * rstd * ga[j] + be[j];
+      sc[j] = rstd * ga[j];
+      sh[j] = be[j] - mean * rstd * ga[j];
+    }
+  }
+  const long long img = static_cast<long long>(b) * HW * C + my_vec * 8;
+  for (int p = blockIdx.x * pix_per_iter + my_pix; p < HW; p += gridDim.x * pix_per_iter) {
+    float v[8];
+    load8(x + img + static_cast<long long>(p) * C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o = fmaf(v[j], sc[j], sh[j]);
       if (silu) o = silu_f(round16<T>(o));
       v[j] = o;
     }
-    store8(y + e, v);
+    store8(y + img + static_cast<long long>(p) * C, v);
   }
 }
 
@@ -697,7 +730,7 @@ extern "C" int dk_cast_16_to_f32(dk_ctx* ctx, int dtype, const void* x, float* y
   return 0;
 }
 
-extern "C" int dk_groupnorm_ws_floats(int B, int G) { return B * GN_CHUNKS * G * 2; }
+extern "C" int dk_groupnorm_ws_floats(int B, int G) { return B * GN_MAX_CHUNKS * G * 2; }
 
 extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* stats, float* ws, int B, int HW, int C,
                                   int G, float eps, void* stream_) {
@@ -706,12 +739,13 @@ extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* 
   DK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 2048, "dk_groupnorm_stats: C=%d G=%d unsupported", C, G);
   DK_REQUIRE(ws != nullptr, "dk_groupnorm_stats: workspace of dk_groupnorm_ws_floats(B, G) floats required");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  dim3 grid(GN_CHUNKS, B);
+  const int chunks = gn_chunks(HW);
+  dim3 grid(chunks, B);
   DK_DISPATCH(dtype, (groupnorm_partial_kernel<T><<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(
-                         static_cast<const T*>(x), ws, HW, C, G)));
+                         static_cast<const T*>(x), ws, HW, C, G, chunks)));
   DK_LAUNCH_CHECK(ctx);
   groupnorm_finalize_kernel<<<(B * G + 127) / 128, 128, 0, stream>>>(
-      ws, stats, B, G, static_cast<double>(HW) * (C / G), eps);
+      ws, stats, B, G, chunks, static_cast<double>(HW) * (C / G), eps);
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -720,12 +754,17 @@ extern "C" int dk_groupnorm_apply(dk_ctx* ctx, int dtype, const void* x, void* y
                                   const void* beta, int B, int HW, int C, int G, int silu, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_groupnorm_apply: null ctx");
   DK_DTYPE_OK(dtype);
-  DK_REQUIRE(C % 8 == 0 && C % G == 0, "dk_groupnorm_apply: C=%d G=%d unsupported", C, G);
+  DK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 2048, "dk_groupnorm_apply: C=%d G=%d unsupported", C, G);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const long long nvec = static_cast<long long>(B) * HW * C / 8;
-  DK_DISPATCH(dtype, (groupnorm_apply_kernel<T><<<grid_for(nvec, 256, ctx->sm_count), 256, 0, stream>>>(
+  const int pix_per_iter = GN_THREADS / (C / 8);
+  int blocks = (HW + pix_per_iter * 4 - 1) / (pix_per_iter * 4);   // >= 4 pixels per thread
+  const int cap = (ctx->sm_count * 16 + B - 1) / B;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dim3 grid(blocks, B);
+  DK_DISPATCH(dtype, (groupnorm_apply_kernel<T><<<grid, GN_THREADS, 0, stream>>>(
                          static_cast<const T*>(x), static_cast<T*>(y), stats, static_cast<const T*>(gamma),
-                         static_cast<const T*>(beta), B, HW, C, G, silu)));
+                         static_cast<const T*>(beta), HW, C, G, silu)));
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -1,0 +1,231 @@
+// K1 (large shapes) — CTA-pair tcgen05 GEMM: one 256x256 output tile per cluster of two CTAs (the two SMs of a TPC),
+// tcgen05.mma.cta_group::2 with M = 256.
+//
+// Why pairs: with one CTA per tile (gemm.cu, 128x256) every k-block pulls 48 KB from L2 into one SM per 512 MMA cycles
+// (96 B/clk/SM) and only four 48 KB stages fit in shared memory; ncu showed the tensor pipe 73 % active with the issuer
+// waiting on TMA.  In pair mode each CTA loads its own 128 A rows plus HALF of the 256 W rows (32 KB per k-block,
+// 64 B/clk/SM, six stages) and the tensor cores of both SMs read the W halves from both shared memories.
+//
+// Per CTA (384 threads, same roles as gemm.cu):
+//   warp 0  TMA producer : A_r (128x64) and W_r (128x64) tiles; transaction bytes are signalled on the LEADER's
+//                          (cluster rank 0) full barrier
+//   warp 1  MMA issuer   : leader only; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs
+//   warp 2  TMEM allocator (cta_group::2 allocation in both CTAs)
+//   warps 4-11 epilogue  : each CTA drains its own 128 rows (gemm_epilogue.cuh); "accumulator drained" arrives on the
+//                          leader's barrier (remote arrive from rank 1)
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include "host.h"
+
+namespace dk {
+
+constexpr int G2_BM = 128;      // rows per CTA (256 per pair)
+constexpr int G2_BN = 256;      // tile columns (each CTA loads 128 of the W rows)
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 6;
+constexpr int G2_THREADS = 384;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
+constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
+constexpr int G2_SMEM_BYTES = G2_STAGES * (G2_A_BYTES + G2_B_BYTES) + 256 + 1024;
+constexpr int G2_TMEM_COLS = 512;                      // two 256-column accumulators
+
+template <typename T>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape s,
+                const GemmEpi e) {
+  using H16 = Half16<T>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + G2_STAGES * G2_A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * (G2_A_BYTES + G2_B_BYTES));
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tfull_bar = empty_bar + G2_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair_id = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int total_tiles = s.num_m * s.num_n;  // num_m counts 256-row tiles here
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < G2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);    // (leader's copy is the live one) one arrive.expect_tx per CTA of the pair
+      mbar_init(&empty_bar[i], 1);   // multicast commit from the leader's MMA thread
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);       // multicast commit
+      mbar_init(&tempty_bar[i], 512);    // (leader's copy) 256 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();   // barriers of both CTAs initialised before any remote arrive / multicast commit
+  if (warp == 2) {
+    tmem_alloc_pair(tmem_slot, G2_TMEM_COLS);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  constexpr int GM = 8;  // grouped rasterisation over 256-row tiles (same band of A rows shared by the pairs in flight)
+  auto decode_tile = [&](int tile, int& m_blk, int& n_blk) {
+    const int group_size = GM * s.num_n;
+    const int group = tile / group_size;
+    const int first_m = group * GM;
+    const int gsz = min(s.num_m - first_m, GM);
+    const int in_group = tile - group * group_size;
+    m_blk = first_m + in_group % gsz;
+    n_blk = in_group / gsz;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer (both CTAs)
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        decode_tile(tile, m_blk, n_blk);
+        const int a_row = m_blk * 256 + static_cast<int>(rank) * G2_BM;
+        const int b_row = n_blk * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
+        for (int kb = 0; kb < s.num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          mbar_arrive_expect_tx_cluster(full_leader, G2_A_BYTES + G2_B_BYTES);
+          tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, full_leader, kb * G2_BK, a_row);
+          tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, full_leader, kb * G2_BK, b_row);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = make_idesc_f16(256, G2_BN, H16::is_bf16, false, false);
+      uint32_t stage = 0, phase = 0;
+      uint32_t it = 0;
+      for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+        const uint32_t acc = it & 1u;
+        const uint32_t acc_phase = (it >> 1) & 1u;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * G2_BN;
+        for (int kb = 0; kb < s.num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * G2_A_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * G2_B_BYTES);
+#pragma unroll
+          for (int k = 0; k < G2_BK / 16; ++k) {
+            umma_ss_pair(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                         make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);
+          if (kb == s.num_k - 1) umma_commit_pair(&tfull_bar[acc], 3);
+          if (++stage == G2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: this CTA's 128 rows of the tile
+    const int quarter = warp & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int NCH = G2_BN / 64;
+    const int r_in_tile = quarter * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
+      int m_blk, n_blk;
+      decode_tile(tile, m_blk, n_blk);
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      const int m = m_blk * 256 + static_cast<int>(rank) * G2_BM + r_in_tile;
+      const bool row_ok = m < s.M;
+      const int batch = m / e.rpb;
+      const int in_b = m - batch * e.rpb;
+      const int pos = e.out_row_off + in_b;
+      const long long orow = static_cast<long long>(batch) * e.out_batch_rows + e.out_row_off + in_b;
+      const long long rrow = static_cast<long long>(batch) * e.res_batch_rows + e.res_row_off + in_b;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * G2_BN + half * (G2_BN / 2);
+      const int n_half0 = n_blk * G2_BN + half * (G2_BN / 2);
+      const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
+      auto release_acc = [&]() {
+        tc_fence_before();
+        mbar_arrive_cluster(tempty_leader);
+      };
+      gemm_epilogue_drain<T, NCH, 0>(s, e, t_row, n_half0, row_ok, orow, rrow, batch, pos, release_acc);
+    }
+  }
+
+  // nobody leaves while the peer may still signal its barriers or read its shared memory
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, G2_TMEM_COLS);
+  }
+}
+
+template <typename T>
+static int launch_gemm2(dk_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
+                        const GemmEpi& e, cudaStream_t stream) {
+  auto kern = gemm2_tc_kernel<T>;
+  static bool configured = false;
+  if (!configured) {
+    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    configured = true;
+  }
+  const int total = s.num_m * s.num_n;
+  const int max_pairs = ctx->sm_count / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  kern<<<2 * pairs, G2_THREADS, G2_SMEM_BYTES, stream>>>(tmA, tmB, s, e);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+}  // namespace dk
+
+// Called by dk_gemm (gemm.cu) for shapes that fill the machine with 256x256 tiles.
+int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, const void* W, long long ldw, int M, int N,
+                        int K, const dk::GemmEpi& e, cudaStream_t stream) {
+  using namespace dk;
+  GemmShape s;
+  s.M = M;
+  s.N = N;
+  s.K = K;
+  s.num_m = dk_ceil_div(M, 256);
+  s.num_n = dk_ceil_div(N, G2_BN);
+  s.num_k = dk_ceil_div(K, G2_BK);
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
+    const uint32_t box[2] = {G2_BK, G2_BM};
+    if (int rc = dk_make_tmap_16b(ctx, &tmA, A, 2, dims, strides, box)) return rc;
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {G2_BK, G2_BN / 2};
+    if (int rc = dk_make_tmap_16b(ctx, &tmB, W, 2, dims, strides, box)) return rc;
+  }
+  if (dtype == DK_BF16) return launch_gemm2<__nv_bfloat16>(ctx, tmA, tmB, s, e, stream);
+  return launch_gemm2<__half>(ctx, tmA, tmB, s, e, stream);
+}

@@ -301,6 +301,24 @@ def check_qk_norm_rope():
     return out
 
 
+def check_gemm_pair_kernel():
+    """the CTA-pair (cta_group::2, 256x256 tile) GEMM forced for every legal shape (DK_GEMM_PAIR=2): ragged M/N/K,
+    every epilogue, multi-wave persistence"""
+    os.environ["DK_GEMM_PAIR"] = "2"
+    _setup()
+    out = {}
+    for (M, N, K) in [(256, 256, 64), (256, 512, 512), (300, 264, 200), (77, 64, 64), (1000, 3072, 1536),
+                      (4352, 768, 3072), (20, 1024, 3072)]:
+        out[f"{M}x{N}x{K}"] = _gemm_case(M, N, K, torch.bfloat16, name=f"pair_{M}x{N}x{K}")
+    out["large"] = _gemm_case(8192, 4608, 1024, torch.bfloat16, bias=True, name="pair_8192x4608x1024")
+    out["gelu"] = _gemm_case(384, 512, 256, torch.bfloat16, bias=True, act=ACT_GELU_ERF, name="pair_gelu")
+    out["remap"] = _gemm_case(600, 512, 256, torch.bfloat16, bias=True, gate=True, res=True, remap=True,
+                              name="pair_remap")
+    out["fp16"] = _gemm_case(300, 512, 320, torch.float16, bias=True, name="pair_fp16")
+    out.update({"qk_" + k: v for k, v in check_gemm_fused_qk_norm_rope().items()})
+    return out
+
+
 def check_gemm_fused_qk_norm_rope():
     """packed QKV projection with the QK-RMSNorm + RoPE epilogue == plain GEMM followed by dk_qk_norm_rope,
     and == an fp32 torch evaluation"""
@@ -449,7 +467,8 @@ def check_softmax_image_post():
 
 ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
-    check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope, check_conv3x3,
+    check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
+    check_gemm_pair_kernel, check_conv3x3,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
     check_attention_v1_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
