@@ -76,7 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 256);
+      mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -222,7 +222,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       auto release_acc = [&]() {
         // accumulator columns of this warp fully drained into registers: hand the TMEM buffer back to the MMA warp
         tc_fence_before();
-        mbar_arrive(&tempty_bar[acc]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       };
 
       gemm_epilogue_drain<T, NCH, MODE>(s, e, t_row, n_half0, row_ok, orow, rrow, batch, pos, release_acc);

@@ -63,7 +63,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);       // multicast commit
-      mbar_init(&tempty_bar[i], 512);    // (leader's copy) 256 epilogue threads of each CTA
+      mbar_init(&tempty_bar[i], 16);     // (leader's copy) one arrive per epilogue warp of each CTA
     }
     fence_barrier_init();
   }
@@ -168,7 +168,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[acc]), 0);
       auto release_acc = [&]() {
         tc_fence_before();
-        mbar_arrive_cluster(tempty_leader);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader);
       };
       gemm_epilogue_drain<T, NCH, 0>(s, e, t_row, n_half0, row_ok, orow, rrow, batch, pos, release_acc);
     }
