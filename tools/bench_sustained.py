@@ -20,30 +20,30 @@ SHAPES = [(16384, 9216, 3072), (16384, 3072, 3072), (16384, 12288, 3072), (16384
 NW = 6  # weight sets per shape
 
 
-def smi():
-    out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits"],
-                         capture_output=True, text=True).stdout.strip().split(",")
-    return float(out[0]), float(out[1])
-
-
-def run(fn, seconds):
-    for _ in range(2):
-        fn(0)
+def run(fn, iters):
+    """enqueue `iters` sequences back to back (no host sync inside), sample clocks/power in the background"""
+    for i in range(3):
+        fn(i)
     torch.cuda.synchronize()
-    t0 = time.time()
-    it = 0
-    clocks = []
+    q = "clocks.sm,power.draw"
+    proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                            stdout=subprocess.PIPE, text=True)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    while time.time() - t0 < seconds:
-        for _ in range(4):
-            fn(it)
-            it += 1
-        clocks.append(smi())
-        torch.cuda.synchronize()
+    for i in range(iters):
+        fn(i)
     e.record()
     torch.cuda.synchronize()
-    return it, s.elapsed_time(e) / 1e3, clocks
+    proc.terminate()
+    lines = proc.stdout.read().strip().splitlines()
+    clocks = []
+    for l in lines[2:]:
+        try:
+            a, b = l.split(",")
+            clocks.append((float(a), float(b)))
+        except ValueError:
+            pass
+    return iters, s.elapsed_time(e) / 1e3, clocks or [(0.0, 0.0)]
 
 
 def main():
@@ -65,7 +65,7 @@ def main():
             torch.matmul(A, Ws[i % NW].t(), out=out)
 
     for name, fn in [("ours", ours), ("cublas", cublas), ("ours_again", ours)]:
-        it, sec, clocks = run(fn, 5.0)
+        it, sec, clocks = run(fn, 500)
         mhz = sorted(c[0] for c in clocks)[len(clocks) // 2]
         watts = sorted(c[1] for c in clocks)[len(clocks) // 2]
         res[name] = {"tflops": flops_seq * it / sec / 1e12, "sm_mhz_median": mhz, "power_w_median": watts, "iters": it}
