@@ -393,65 +393,84 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   if (warp < 4) {
     // producer warpgroup: give its registers to the softmax warpgroups
     setmaxnreg_dec<112>();
-    if (warp == 0 && lane == 0) {
-      // ------------------------------------------------------------------ TMA producer
-      mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
 #pragma unroll
-      for (int w = 0; w < 2; ++w)
+        for (int w = 0; w < 2; ++w)
 #pragma unroll
-        for (int a = 0; a < D / 64; ++a)
-          tma_load_2d(sQ + w * Cfg::TILE_BYTES + a * 16384, &tmQKV, q_full, head * D + a * 64,
-                      row_base + q0 + w * ATT_BQ);
+          for (int a = 0; a < D / 64; ++a)
+            tma_load_2d(sQ + w * Cfg::TILE_BYTES + a * 16384, &tmQKV, q_full, head * D + a * 64,
+                        row_base + q0 + w * ATT_BQ);
+      }
+      __syncwarp();
       int st = 0;
       uint32_t par = 0;
       for (int j = 0; j < n_tiles; ++j) {
         const int kv_row = row_base + j * ATT_BKV;
         mbar_wait(&k_empty[st], par ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
 #pragma unroll
-        for (int a = 0; a < D / 64; ++a)
-          tma_load_2d(sK + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &k_full[st], h + head * D + a * 64, kv_row);
+          for (int a = 0; a < D / 64; ++a)
+            tma_load_2d(sK + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &k_full[st], h + head * D + a * 64, kv_row);
+        }
+        __syncwarp();
         mbar_wait(&v_empty[st], par ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
 #pragma unroll
-        for (int a = 0; a < D / 64; ++a)
-          tma_load_2d(sV + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &v_full[st], 2 * h + head * D + a * 64, kv_row);
+          for (int a = 0; a < D / 64; ++a)
+            tma_load_2d(sV + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &v_full[st], 2 * h + head * D + a * 64, kv_row);
+        }
+        __syncwarp();
         if (++st == KS) {
           st = 0;
           par ^= 1;
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer (converged warp, elected issue)
       constexpr uint32_t idesc_qk = make_idesc_f16(ATT_BQ, ATT_BKV, H16::is_bf16, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(ATT_BQ, D, H16::is_bf16, false, true);
+      const uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      const uint32_t q_lo0 = smem_desc_lo(smem_u32(sQ), 0);
+      const uint32_t k_lo0 = smem_desc_lo(smem_u32(sK), 0);
+      const uint32_t v_lo0 = smem_desc_lo(smem_u32(sV), 16384);   // MN-major: LBO = stride between 64-wide d atoms
+      constexpr uint32_t TILE16 = Cfg::TILE_BYTES >> 4;
+      // S_w = Q_w K^T : K = d in 16-wide slices (slice k lives in 64-column atom k>>2 at +32 B * (k&3))
       auto issue_qk = [&](int w, int st) {
-        const uint32_t q_addr = smem_u32(sQ + w * Cfg::TILE_BYTES);
-        const uint32_t k_addr = smem_u32(sK + st * Cfg::TILE_BYTES);
+        const uint32_t q_lo = q_lo0 + w * TILE16;
+        const uint32_t k_lo = k_lo0 + st * TILE16;
         const uint32_t d_tmem = tmem_base + Cfg::TMEM_S + w * 128;
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 0, 1024), make_smem_desc_sw128(k_addr + off, 0, 1024),
-                  idesc_qk, k != 0 ? 1u : 0u);
+          const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, smem_desc_join(q_lo + off, desc_hi), smem_desc_join(k_lo + off, desc_hi), idesc_qk,
+                  k != 0 ? 1u : 0u);
         }
         umma_commit(&s_full[w]);
       };
+      // O_w += P_w V : A = P_w from TMEM (16 keys = 8 columns per slice), B = V slice of 16 key rows (2048 B apart)
       auto issue_pv = [&](int w, int st, bool first) {
-        const uint32_t v_addr = smem_u32(sV + st * Cfg::TILE_BYTES);
-        const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + w * 128;   // P_w: 16-bit pairs in S_w's first 64 columns
+        const uint32_t v_lo = v_lo0 + st * TILE16;
+        const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + w * 128;
         const uint32_t d_tmem = tmem_base + Cfg::TMEM_O + w * 128;
 #pragma unroll
         for (int k = 0; k < ATT_BKV / 16; ++k)
-          umma_ts(d_tmem, p_tmem + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv,
+          umma_ts(d_tmem, p_tmem + k * 8, smem_desc_join(v_lo + k * (2048 >> 4), desc_hi), idesc_pv,
                   (!first || k != 0) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      umma_commit(&k_empty[0]);
+      if (elect_one_sync()) {
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        umma_commit(&k_empty[0]);
+      }
+      __syncwarp();
       int st = 0;
       uint32_t par = 0;
       for (int j = 0; j < n_tiles; ++j) {
@@ -460,23 +479,26 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         const bool more = j + 1 < n_tiles;
         mbar_wait(&v_full[st], par);
         mbar_wait(&p_full[0], j & 1);
+        if (more) mbar_wait(&k_full[st_n], par_n);
         tc_fence_after();
-        issue_pv(0, st, j == 0);
-        if (!more) umma_commit(&o_full[0]);
-        if (more) {
-          mbar_wait(&k_full[st_n], par_n);
-          tc_fence_after();
-          issue_qk(0, st_n);
+        if (elect_one_sync()) {
+          issue_pv(0, st, j == 0);
+          if (!more) umma_commit(&o_full[0]);
+          if (more) issue_qk(0, st_n);
         }
+        __syncwarp();
         mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
-        issue_pv(1, st, j == 0);
-        umma_commit(&v_empty[st]);
-        if (!more) umma_commit(&o_full[1]);
-        if (more) {
-          issue_qk(1, st_n);
-          umma_commit(&k_empty[st_n]);
+        if (elect_one_sync()) {
+          issue_pv(1, st, j == 0);
+          umma_commit(&v_empty[st]);
+          if (!more) umma_commit(&o_full[1]);
+          if (more) {
+            issue_qk(1, st_n);
+            umma_commit(&k_empty[st_n]);
+          }
         }
+        __syncwarp();
         st = st_n;
         par = par_n;
       }

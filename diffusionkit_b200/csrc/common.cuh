@@ -255,6 +255,30 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// Split form for issue loops: the high word is loop invariant, the low word is (LBO field | start address >> 4); stepping
+// through stages / K slices is one integer add on the low word.
+__device__ __forceinline__ uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// One lane of a converged warp (the tcgen05 / TMA issue idiom: the whole warp runs the loop so addresses stay in
+// uniform registers; only the issue itself is predicated on the elected lane).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // Instruction descriptor for kind::f16 (fp16/bf16 in, fp32 accumulate).
 //   [4,6) c format (1 = f32); [7,10) a format (0 = f16, 1 = bf16); [10,13) b format;
 //   [15] a major (0 = K, 1 = MN); [16] b major; [17,23) N >> 3; [24,29) M >> 4.

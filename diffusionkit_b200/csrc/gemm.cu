@@ -103,22 +103,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int m_blk, n_blk;
-        decode_tile(tile, m_blk, n_blk);
-        int img = 0, y0 = 0, x0 = 0;
-        if (MODE == 1) {
-          const int per_img = g.tiles_x * g.tiles_y;
-          img = m_blk / per_img;
-          const int t = m_blk - img * per_img;
-          y0 = (t / g.tiles_x) * g.TH;
-          x0 = (t % g.tiles_x) * g.TW;
-        }
-        for (int kb = 0; kb < s.num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------------------------ TMA producer, converged warp
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      decode_tile(tile, m_blk, n_blk);
+      int img = 0, y0 = 0, x0 = 0;
+      if (MODE == 1) {
+        const int per_img = g.tiles_x * g.tiles_y;
+        img = m_blk / per_img;
+        const int t = m_blk - img * per_img;
+        y0 = (t / g.tiles_x) * g.TH;
+        x0 = (t % g.tiles_x) * g.TW;
+      }
+      for (int kb = 0; kb < s.num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           uint8_t* a_dst = sA + stage * A_BYTES;
           uint8_t* b_dst = sB + stage * B_BYTES;
@@ -137,43 +137,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d(b_dst + j * (BK * 128), &tmB, &full_bar[stage], n_blk * BN + j * 64, kb * BK);
           }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, H16::is_bf16, false, B_MN);
-      uint32_t stage = 0, phase = 0;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t acc = it & 1u;
-        const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+    // -------------------------------------------------------------------- MMA issuer, converged warp
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, H16::is_bf16, false, B_MN);
+    const uint32_t desc_hi = smem_desc_hi_sw128(1024);
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA), 0);
+    const uint32_t b_lo0 = smem_desc_lo(smem_u32(sB), B_MN ? BK * 128 : 0);
+    uint32_t stage = 0, phase = 0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      const uint32_t acc_phase = (it >> 1) & 1u;
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < s.num_k; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < s.num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * B_BYTES);
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + stage * (A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + stage * (B_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_addr + k * (UMMA_K * 2), 0, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_addr + k * (UMMA_K * 128), BK * 128, 1024)
-                                        : make_smem_desc_sw128(b_addr + k * (UMMA_K * 2), 0, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_ss(d_tmem, smem_desc_join(a_lo + k * ((UMMA_K * 2) >> 4), desc_hi),
+                    smem_desc_join(b_lo + k * ((B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4), desc_hi), idesc,
+                    (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);                        // smem stage reusable once these MMAs retire
           if (kb == s.num_k - 1) umma_commit(&tfull_bar[acc]);   // accumulator complete
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }

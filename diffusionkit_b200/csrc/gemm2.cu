@@ -13,6 +13,8 @@
 //   warp 2  TMEM allocator (cta_group::2 allocation in both CTAs)
 //   warps 4-11 epilogue  : each CTA drains its own 128 rows (gemm_epilogue.cuh); "accumulator drained" arrives on the
 //                          leader's barrier (remote arrive from rank 1)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "host.h"
@@ -20,20 +22,28 @@
 namespace dk {
 
 constexpr int G2_BM = 128;      // rows per CTA (256 per pair)
-constexpr int G2_BN = 256;      // tile columns (each CTA loads 128 of the W rows)
 constexpr int G2_BK = 64;
-constexpr int G2_STAGES = 6;
 constexpr int G2_THREADS = 384;
 constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
-constexpr int G2_B_BYTES = (G2_BN / 2) * G2_BK * 2;    // 16 KB
-constexpr int G2_SMEM_BYTES = G2_STAGES * (G2_A_BYTES + G2_B_BYTES) + 256 + 1024;
-constexpr int G2_TMEM_COLS = 512;                      // two 256-column accumulators
 
-template <typename T>
+// G2_BN: tile columns (each CTA loads half of the W rows).  256 is the default; 192 / 128 exist so that GEMMs whose
+// 256-wide tile count is a poor multiple of the 74 CTA pairs (N = 3072: 10.4 waves) can be re-tiled (192: 13.8 waves).
+template <int G2_BN>
+struct G2Cfg {
+  static constexpr int STAGES = G2_BN == 256 ? 6 : (G2_BN == 192 ? 7 : 8);
+  static constexpr int B_BYTES = (G2_BN / 2) * G2_BK * 2;
+  static constexpr int SMEM_BYTES = STAGES * (G2_A_BYTES + B_BYTES) + 256 + 1024;
+  static constexpr int TMEM_COLS = G2_BN > 128 ? 512 : 256;   // two accumulators, power-of-two allocation
+};
+
+template <typename T, int G2_BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape s,
                 const GemmEpi e) {
   using H16 = Half16<T>;
+  constexpr int G2_STAGES = G2Cfg<G2_BN>::STAGES;
+  constexpr int G2_B_BYTES = G2Cfg<G2_BN>::B_BYTES;
+  constexpr int G2_TMEM_COLS = G2Cfg<G2_BN>::TMEM_COLS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
@@ -89,31 +99,35 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer (both CTAs)
-      uint32_t stage = 0, phase = 0;
-      for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
-        int m_blk, n_blk;
-        decode_tile(tile, m_blk, n_blk);
-        const int a_row = m_blk * 256 + static_cast<int>(rank) * G2_BM;
-        const int b_row = n_blk * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
-        for (int kb = 0; kb < s.num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ---------------------------------------------------------------- TMA producer (both CTAs), converged warp
+    uint32_t stage = 0, phase = 0;
+    for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      decode_tile(tile, m_blk, n_blk);
+      const int a_row = m_blk * 256 + static_cast<int>(rank) * G2_BM;
+      const int b_row = n_blk * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
+      for (int kb = 0; kb < s.num_k; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one_sync()) {
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           mbar_arrive_expect_tx_cluster(full_leader, G2_A_BYTES + G2_B_BYTES);
           tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, full_leader, kb * G2_BK, a_row);
           tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, full_leader, kb * G2_BK, b_row);
-          if (++stage == G2_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == G2_STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ---------------------------------------------------------------- MMA issuer (leader CTA only)
+    if (leader) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA only), converged warp
       constexpr uint32_t idesc = make_idesc_f16(256, G2_BN, H16::is_bf16, false, false);
+      const uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(sA), 0);
+      const uint32_t b_lo0 = smem_desc_lo(smem_u32(sB), 0);
       uint32_t stage = 0, phase = 0;
       uint32_t it = 0;
       for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
@@ -125,15 +139,17 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < s.num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + stage * G2_A_BYTES);
-          const uint32_t b_addr = smem_u32(sB + stage * G2_B_BYTES);
+          if (elect_one_sync()) {
+            const uint32_t a_lo = a_lo0 + stage * (G2_A_BYTES >> 4);
+            const uint32_t b_lo = b_lo0 + stage * (G2_B_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < G2_BK / 16; ++k) {
-            umma_ss_pair(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
-                         make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < G2_BK / 16; ++k)
+              umma_ss_pair(d_tmem, smem_desc_join(a_lo + k * 2, desc_hi), smem_desc_join(b_lo + k * 2, desc_hi), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+            umma_commit_pair(&empty_bar[stage], 3);
+            if (kb == s.num_k - 1) umma_commit_pair(&tfull_bar[acc], 3);
           }
-          umma_commit_pair(&empty_bar[stage], 3);
-          if (kb == s.num_k - 1) umma_commit_pair(&tfull_bar[acc], 3);
+          __syncwarp();
           if (++stage == G2_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -184,21 +200,46 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-template <typename T>
+template <typename T, int G2_BN>
 static int launch_gemm2(dk_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
                         const GemmEpi& e, cudaStream_t stream) {
-  auto kern = gemm2_tc_kernel<T>;
+  auto kern = gemm2_tc_kernel<T, G2_BN>;
   static bool configured = false;
   if (!configured) {
-    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2Cfg<G2_BN>::SMEM_BYTES));
     configured = true;
   }
   const int total = s.num_m * s.num_n;
   const int max_pairs = ctx->sm_count / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
-  kern<<<2 * pairs, G2_THREADS, G2_SMEM_BYTES, stream>>>(tmA, tmB, s, e);
+  kern<<<2 * pairs, G2_THREADS, G2Cfg<G2_BN>::SMEM_BYTES, stream>>>(tmA, tmB, s, e);
   DK_LAUNCH_CHECK(ctx);
   return 0;
+}
+
+// tile width with the fewest (rounds x width) over the 74 CTA pairs; narrower tiles pay a small efficiency penalty
+static int pick_pair_bn(const dk_ctx* ctx, int M, int N, bool need_256) {
+  if (need_256) return 256;
+  static const int force = [] {
+    const char* v = getenv("DK_GEMM_PAIR_BN");
+    return v ? atoi(v) : 0;
+  }();
+  if (force == 256 || force == 192 || force == 128) return force;
+  const int pairs = ctx->sm_count / 2;
+  const int cand[3] = {256, 192, 128};
+  const double penalty[3] = {1.0, 1.03, 1.08};
+  int best = 256;
+  double best_cost = 1e30;
+  for (int i = 0; i < 3; ++i) {
+    const long long tiles = static_cast<long long>(dk_ceil_div(M, 256)) * dk_ceil_div(N, cand[i]);
+    const long long rounds = (tiles + pairs - 1) / pairs;
+    const double cost = static_cast<double>(rounds) * cand[i] * penalty[i];
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = cand[i];
+    }
+  }
+  return best;
 }
 
 }  // namespace dk
@@ -207,12 +248,13 @@ static int launch_gemm2(dk_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
 int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, const void* W, long long ldw, int M, int N,
                         int K, const dk::GemmEpi& e, cudaStream_t stream) {
   using namespace dk;
+  const int bn = pick_pair_bn(ctx, M, N, e.qk_d != 0);
   GemmShape s;
   s.M = M;
   s.N = N;
   s.K = K;
   s.num_m = dk_ceil_div(M, 256);
-  s.num_n = dk_ceil_div(N, G2_BN);
+  s.num_n = dk_ceil_div(N, bn);
   s.num_k = dk_ceil_div(K, G2_BK);
   CUtensorMap tmA, tmB;
   {
@@ -224,9 +266,15 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {G2_BK, G2_BN / 2};
+    const uint32_t box[2] = {G2_BK, static_cast<uint32_t>(bn / 2)};
     if (int rc = dk_make_tmap_16b(ctx, &tmB, W, 2, dims, strides, box)) return rc;
   }
-  if (dtype == DK_BF16) return launch_gemm2<__nv_bfloat16>(ctx, tmA, tmB, s, e, stream);
-  return launch_gemm2<__half>(ctx, tmA, tmB, s, e, stream);
+  if (dtype == DK_BF16) {
+    if (bn == 256) return launch_gemm2<__nv_bfloat16, 256>(ctx, tmA, tmB, s, e, stream);
+    if (bn == 192) return launch_gemm2<__nv_bfloat16, 192>(ctx, tmA, tmB, s, e, stream);
+    return launch_gemm2<__nv_bfloat16, 128>(ctx, tmA, tmB, s, e, stream);
+  }
+  if (bn == 256) return launch_gemm2<__half, 256>(ctx, tmA, tmB, s, e, stream);
+  if (bn == 192) return launch_gemm2<__half, 192>(ctx, tmA, tmB, s, e, stream);
+  return launch_gemm2<__half, 128>(ctx, tmA, tmB, s, e, stream);
 }

@@ -311,6 +311,8 @@ def check_gemm_pair_kernel():
                       (4352, 768, 3072), (20, 1024, 3072)]:
         out[f"{M}x{N}x{K}"] = _gemm_case(M, N, K, torch.bfloat16, name=f"pair_{M}x{N}x{K}")
     out["large"] = _gemm_case(8192, 4608, 1024, torch.bfloat16, bias=True, name="pair_8192x4608x1024")
+    out["bn192"] = _gemm_case(4096, 3072, 512, torch.bfloat16, bias=True, name="pair_4096x3072x512")      # re-tiled 192
+    out["bn128"] = _gemm_case(1024, 1152, 256, torch.bfloat16, bias=True, gate=True, res=True, name="pair_1024x1152")
     out["gelu"] = _gemm_case(384, 512, 256, torch.bfloat16, bias=True, act=ACT_GELU_ERF, name="pair_gelu")
     out["remap"] = _gemm_case(600, 512, 256, torch.bfloat16, bias=True, gate=True, res=True, remap=True,
                               name="pair_remap")
