@@ -334,7 +334,8 @@ struct Att2Cfg {
   static constexpr int TMEM_O = 256;   // + 128 * w
 };
 
-template <typename T, int D>
+// POLY: how many of every four exponentials are evaluated on the FMA pipe (ex2_poly) instead of MUFU.EX2
+template <typename T, int D, int POLY>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
   using H16 = Half16<T>;
@@ -567,8 +568,10 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       }
       // pass 2: P = exp2(s * sl2 - m_run), packed two 16-bit values per 32-bit TMEM column (key 2i in the low half),
       // written over the first 64 columns of this warpgroup's own S accumulator
-      float ls0 = 0.f, ls1 = 0.f;
+      float2 lsum = make_float2(0.f, 0.f);
       uint32_t pk[2][32];
+      const float2 sl2v = make_float2(sl2, sl2);
+      const float2 negm = make_float2(-m_run, -m_run);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t sa[32], sb[32];
@@ -586,12 +589,13 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
             if (k0 + 32 >= kv_valid) b0 = -INFINITY;
             if (k0 + 33 >= kv_valid) b1 = -INFINITY;
           }
-          const float e0 = ex2_approx(fmaf(a0, sl2, -m_run));
-          const float e1 = ex2_approx(fmaf(a1, sl2, -m_run));
-          const float f0 = ex2_approx(fmaf(b0, sl2, -m_run));
-          const float f1 = ex2_approx(fmaf(b1, sl2, -m_run));
-          ls0 += e0 + f0;
-          ls1 += e1 + f1;
+          const float2 xa = ffma2(make_float2(a0, a1), sl2v, negm);
+          const float2 xb = ffma2(make_float2(b0, b1), sl2v, negm);
+          const float e0 = ex2_approx(xa.x);
+          const float e1 = (POLY >= 2) ? ex2_poly(xa.y) : ex2_approx(xa.y);
+          const float f0 = ex2_approx(xb.x);
+          const float f1 = (POLY >= 1) ? ex2_poly(xb.y) : ex2_approx(xb.y);
+          lsum = fadd2(lsum, fadd2(make_float2(e0, e1), make_float2(f0, f1)));
           pk[half][i] = H16::pack(e0, e1);
           pk[half][16 + i] = H16::pack(f0, f1);
         }
@@ -599,7 +603,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       // all reads of S_w by this thread are complete (wait::ld above) before P overwrites its first 64 columns
       tmem_st_32x32(t_s, pk[0]);
       tmem_st_32x32(t_s + 32, pk[1]);
-      l_run += ls0 + ls1;
+      l_run += lsum.x + lsum.y;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[w]);
@@ -646,10 +650,10 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   }
 }
 
-template <typename T, int D>
-static int launch_attention_v2(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+template <typename T, int D, int POLY>
+static int launch_attention_v2p(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
   using Cfg = Att2Cfg<D>;
-  auto kern = attention_fwd_v2_kernel<T, D>;
+  auto kern = attention_fwd_v2_kernel<T, D, POLY>;
   static bool configured = false;
   if (!configured) {
     DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -674,6 +678,17 @@ static int launch_attention(dk_ctx* ctx, const CUtensorMap& tm, const AttParams&
   kern<<<grid, ATT_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, p);
   DK_LAUNCH_CHECK(ctx);
   return 0;
+}
+
+template <typename T, int D>
+static int launch_attention_v2(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+  static const int poly = [] {
+    const char* e = getenv("DK_ATT_POLY");
+    return e ? atoi(e) : 1;
+  }();
+  if (poly <= 0) return launch_attention_v2p<T, D, 0>(ctx, tm, p, stream);
+  if (poly == 1) return launch_attention_v2p<T, D, 1>(ctx, tm, p, stream);
+  return launch_attention_v2p<T, D, 2>(ctx, tm, p, stream);
 }
 
 }  // namespace dk
@@ -710,7 +725,8 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
   p.ld0 = ld0;
   p.out1 = out1;
   p.ld1 = ld1;
-  // DK_ATTENTION_V1=1 selects the single-Q-tile kernel with P staged through shared memory (kept for A/B checks)
+  // DK_ATT_POLY (0..2, default 1): share of the softmax exponentials evaluated on the FMA pipe (tuning knob)
+// DK_ATTENTION_V1=1 selects the single-Q-tile kernel with P staged through shared memory (kept for A/B checks)
   static const bool use_v1 = [] {
     const char* e = getenv("DK_ATTENTION_V1");
     return e != nullptr && e[0] == '1';
