@@ -568,10 +568,8 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       }
       // pass 2: P = exp2(s * sl2 - m_run), packed two 16-bit values per 32-bit TMEM column (key 2i in the low half),
       // written over the first 64 columns of this warpgroup's own S accumulator
-      float2 lsum = make_float2(0.f, 0.f);
+      float ls0 = 0.f, ls1 = 0.f;
       uint32_t pk[2][32];
-      const float2 sl2v = make_float2(sl2, sl2);
-      const float2 negm = make_float2(-m_run, -m_run);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t sa[32], sb[32];
@@ -589,13 +587,15 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
             if (k0 + 32 >= kv_valid) b0 = -INFINITY;
             if (k0 + 33 >= kv_valid) b1 = -INFINITY;
           }
-          const float2 xa = ffma2(make_float2(a0, a1), sl2v, negm);
-          const float2 xb = ffma2(make_float2(b0, b1), sl2v, negm);
-          const float e0 = ex2_approx(xa.x);
-          const float e1 = (POLY >= 2) ? ex2_poly(xa.y) : ex2_approx(xa.y);
-          const float f0 = ex2_approx(xb.x);
-          const float f1 = (POLY >= 1) ? ex2_poly(xb.y) : ex2_approx(xb.y);
-          lsum = fadd2(lsum, fadd2(make_float2(e0, e1), make_float2(f0, f1)));
+          // (packed fma.rn.f32x2 / add.rn.f32x2 were measured slower here: 799 vs 947 TFLOP/s at C4)
+          const float xa0 = fmaf(a0, sl2, -m_run), xa1 = fmaf(a1, sl2, -m_run);
+          const float xb0 = fmaf(b0, sl2, -m_run), xb1 = fmaf(b1, sl2, -m_run);
+          const float e0 = ex2_approx(xa0);
+          const float e1 = (POLY >= 2) ? ex2_poly(xa1) : ex2_approx(xa1);
+          const float f0 = ex2_approx(xb0);
+          const float f1 = (POLY >= 1) ? ex2_poly(xb1) : ex2_approx(xb1);
+          ls0 += e0 + f0;
+          ls1 += e1 + f1;
           pk[half][i] = H16::pack(e0, e1);
           pk[half][16 + i] = H16::pack(f0, f1);
         }
@@ -603,7 +603,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       // all reads of S_w by this thread are complete (wait::ld above) before P overwrites its first 64 columns
       tmem_st_32x32(t_s, pk[0]);
       tmem_st_32x32(t_s + 32, pk[1]);
-      l_run += lsum.x + lsum.y;
+      l_run += ls0 + ls1;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_full[w]);

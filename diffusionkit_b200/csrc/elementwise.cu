@@ -59,35 +59,38 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 //     mlx.fast.layer_norm semantics: biased variance, fp32 accumulation, (x-mu)*rsqrt(var+eps)*w + b with
 //     w = 1 + scale, b = shift (reference mlx/mmdit.py:958-972).
 // ------------------------------------------------------------------------------------------------
-constexpr int LN_THREADS = 128;
-constexpr int LN_MAXV = 4;  // h <= 128 * 8 * 4 = 4096
+constexpr int LN_WARPS = 4;     // rows per block
+constexpr int LN_MAXV = 16;     // h <= 32 lanes * 8 * 16 = 4096
 
-template <typename T>
-__global__ void __launch_bounds__(LN_THREADS)
+// One warp per row: the row lives in registers (<= 16 x 128-bit loads in flight per lane), statistics via warp
+// shuffles only — no shared memory, no block barriers.
+template <typename T, int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
 ln_modulate_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ shift, const T* __restrict__ scale,
-                   long long mod_ld, int rows_per_batch, int h, float eps) {
-  __shared__ float red[LN_THREADS / 32];
-  const int row = blockIdx.x;
+                   long long mod_ld, int rows, int rows_per_batch, int h, float eps) {
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
   const int b = row / rows_per_batch;
   const T* xr = x + static_cast<long long>(row) * h;
   T* yr = y + static_cast<long long>(row) * h;
   const int nvec = h / 8;
-  float v[LN_MAXV][8];
+  float v[NV][8];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vec = threadIdx.x + i * LN_THREADS;
+  for (int i = 0; i < NV; ++i) {
+    const int vec = lane + i * 32;
     if (vec < nvec) {
       load8(xr + vec * 8, v[i]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
     }
   }
-  const float mean = block_sum<LN_THREADS>(s, red) / h;
+  const float mean = warp_sum(s) / h;
   float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vec = threadIdx.x + i * LN_THREADS;
+  for (int i = 0; i < NV; ++i) {
+    const int vec = lane + i * 32;
     if (vec < nvec) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -96,12 +99,12 @@ ln_modulate_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restri
       }
     }
   }
-  const float rstd = rsqrtf(block_sum<LN_THREADS>(q, red) / h + eps);
+  const float rstd = rsqrtf(warp_sum(q) / h + eps);
   const T* sh = shift + static_cast<long long>(b) * mod_ld;
   const T* sc = scale + static_cast<long long>(b) * mod_ld;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vec = threadIdx.x + i * LN_THREADS;
+  for (int i = 0; i < NV; ++i) {
+    const int vec = lane + i * 32;
     if (vec < nvec) {
       float a[8], c[8], o[8];
       load8(sc + vec * 8, a);
@@ -565,13 +568,26 @@ extern "C" int dk_ln_modulate(dk_ctx* ctx, int dtype, const void* x, void* y, co
   DK_REQUIRE(ctx != nullptr, "dk_ln_modulate: null ctx");
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(rows > 0 && rows_per_batch > 0, "dk_ln_modulate: empty input");
-  DK_REQUIRE(h % 8 == 0 && h <= LN_THREADS * 8 * LN_MAXV, "dk_ln_modulate: h=%d unsupported (multiple of 8, <= %d)", h,
-             LN_THREADS * 8 * LN_MAXV);
+  DK_REQUIRE(h % 8 == 0 && h <= 32 * 8 * LN_MAXV, "dk_ln_modulate: h=%d unsupported (multiple of 8, <= %d)", h,
+             32 * 8 * LN_MAXV);
   DK_REQUIRE(mod_ld % 8 == 0, "dk_ln_modulate: mod_ld must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DK_DISPATCH(dtype, (ln_modulate_kernel<T><<<rows, LN_THREADS, 0, stream>>>(
-                         static_cast<const T*>(x), static_cast<T*>(y), static_cast<const T*>(shift),
-                         static_cast<const T*>(scale), mod_ld, rows_per_batch, h, eps)));
+  const int blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+  const int nv = (h / 8 + 31) / 32;   // vectors per lane
+  DK_DISPATCH(dtype, {
+    const T* xp = static_cast<const T*>(x);
+    T* yp = static_cast<T*>(y);
+    const T* shp = static_cast<const T*>(shift);
+    const T* scp = static_cast<const T*>(scale);
+    if (nv <= 4)
+      ln_modulate_kernel<T, 4><<<blocks, LN_WARPS * 32, 0, stream>>>(xp, yp, shp, scp, mod_ld, rows, rows_per_batch, h, eps);
+    else if (nv <= 8)
+      ln_modulate_kernel<T, 8><<<blocks, LN_WARPS * 32, 0, stream>>>(xp, yp, shp, scp, mod_ld, rows, rows_per_batch, h, eps);
+    else if (nv <= 12)
+      ln_modulate_kernel<T, 12><<<blocks, LN_WARPS * 32, 0, stream>>>(xp, yp, shp, scp, mod_ld, rows, rows_per_batch, h, eps);
+    else
+      ln_modulate_kernel<T, 16><<<blocks, LN_WARPS * 32, 0, stream>>>(xp, yp, shp, scp, mod_ld, rows, rows_per_batch, h, eps);
+  });
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
