@@ -331,7 +331,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "clocks": clk,
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 GEMM, all nn.Linear of the MMDiT)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "gemm2_tc_kernel / gemm_tc_kernel (tcgen05 GEMMs: every nn.Linear of the MMDiT)",
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved / peaks["bf16_tflops"], "traffic": None,
                      "peak_source": f"{peaks['source']} bf16 burst (sustained {peaks['bf16_tflops_sustained']})",
@@ -394,6 +395,8 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":
