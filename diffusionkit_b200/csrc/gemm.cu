@@ -117,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         x0 = (t % g.tiles_x) * g.TW;
       }
       for (int kb = 0; kb < s.num_k; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_warp(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&full_bar[stage], A_BYTES + B_BYTES);
           uint8_t* a_dst = sA + stage * A_BYTES;
@@ -156,11 +156,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
       const uint32_t acc_phase = (it >> 1) & 1u;
-      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < s.num_k; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+        mbar_wait_warp(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t a_lo = a_lo0 + stage * (A_BYTES >> 4);
@@ -217,7 +217,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         rrow = orow;
       }
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait_warp(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + half * (BN / 2);
       const int n_half0 = n_blk * BN + half * (BN / 2);

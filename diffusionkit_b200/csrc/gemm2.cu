@@ -107,7 +107,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int a_row = m_blk * 256 + static_cast<int>(rank) * G2_BM;
       const int b_row = n_blk * G2_BN + static_cast<int>(rank) * (G2_BN / 2);
       for (int kb = 0; kb < s.num_k; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_warp(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           mbar_arrive_expect_tx_cluster(full_leader, G2_A_BYTES + G2_B_BYTES);
@@ -133,11 +133,11 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int tile = pair_id; tile < total_tiles; tile += num_pairs, ++it) {
         const uint32_t acc = it & 1u;
         const uint32_t acc_phase = (it >> 1) & 1u;
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait_warp(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * G2_BN;
         for (int kb = 0; kb < s.num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_warp(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one_sync()) {
             const uint32_t a_lo = a_lo0 + stage * (G2_A_BYTES >> 4);
@@ -177,7 +177,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const long long orow = static_cast<long long>(batch) * e.out_batch_rows + e.out_row_off + in_b;
       const long long rrow = static_cast<long long>(batch) * e.res_batch_rows + e.res_row_off + in_b;
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      mbar_wait_warp(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * G2_BN + half * (G2_BN / 2);
       const int n_half0 = n_blk * G2_BN + half * (G2_BN / 2);
