@@ -87,7 +87,9 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  constexpr int GM = 8;  // grouped rasterisation over 256-row tiles (same band of A rows shared by the pairs in flight)
+  // grouped rasterisation over 256-row tiles: a band of GM m-tiles is swept across all n-tiles, so W is re-read from
+  // HBM once per band (M/256/GM times in total) while the band's A rows stay L2 resident
+  constexpr int GM = 16;
   auto decode_tile = [&](int tile, int& m_blk, int& n_blk) {
     const int group_size = GM * s.num_n;
     const int group = tile / group_size;

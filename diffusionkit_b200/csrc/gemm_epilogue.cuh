@@ -147,7 +147,7 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmShape& s, const Ge
         o.y = H16::pack(v[2], v[3]);
         o.z = H16::pack(v[4], v[5]);
         o.w = H16::pack(v[6], v[7]);
-        *reinterpret_cast<uint4*>(out + orow * e.ldc + n) = o;
+        __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: do not displace A / W tiles in L2
       }
     }
   }
@@ -211,7 +211,7 @@ for (int chunk = 0; chunk < NCH; ++chunk) {
     o.y = H16::pack(v[2], v[3]);
     o.z = H16::pack(v[4], v[5]);
     o.w = H16::pack(v[6], v[7]);
-    *reinterpret_cast<uint4*>(out + orow * e.ldc + n) = o;
+    __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: do not displace A / W tiles in L2
   }
 }
 }
