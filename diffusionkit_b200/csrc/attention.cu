@@ -521,6 +521,11 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
+      if (p.debug >= 3) {   // timing experiment: pure barrier round trip, no TMEM traffic
+        tc_fence_before();
+        mbar_arrive(&p_full[w]);
+        continue;
+      }
       const int kv_valid = p.S - j * ATT_BKV;   // keys beyond the sequence end exist only on the tail tile
 
       // pass 1 over the S row: running max of the raw scores (the positive scale commutes with max).
