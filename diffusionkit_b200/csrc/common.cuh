@@ -73,6 +73,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Latency-critical wait: non-blocking test_wait in a tight spin (try_wait parks the thread in hardware and its wake-up
+// after the phase completes was measured to cost on the order of a microsecond in dependent producer/consumer chains).
+__device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > DK_WATCHDOG_CYCLES) {
+      printf("[dkb200] mbarrier watchdog (spin): block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+// one spinning lane per warp, the rest parked at the warp barrier
+__device__ __forceinline__ void mbar_wait_spin_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait_spin(bar, parity);
+  __syncwarp();
+}
+
 // Whole-warp wait with a single polling lane: lane 0 spins (hardware-suspended try_wait), the other 31 lanes park at
 // the warp barrier instead of burning issue slots and power on their own polls.
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
