@@ -295,11 +295,14 @@ def run_ours(args):
         return out
 
     ops.gemm = timed_gemm
+    graphs_were = pipe.mmdit.use_cuda_graphs
+    pipe.mmdit.use_cuda_graphs = False          # the instrumented step must launch kernel by kernel
     try:
         latent, _ = pipe.denoise_latents(cond_dev, pooled_dev, num_steps=steps, cfg_weight=cfgw,
                                          latent_size=(lat, lat), seed=seeds, noise=noise_dev)
     finally:
         ops.gemm = orig_gemm
+        pipe.mmdit.use_cuda_graphs = graphs_were
     torch.cuda.synchronize()
     t_gemm = sum(s.elapsed_time(e) for s, e in gemm_stats["events"]) / 1e3
     n_gemm = len(gemm_stats["events"])

@@ -20,6 +20,7 @@ B200 layout decisions (vs. the reference's per-module MLX graph):
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -66,6 +67,9 @@ class MMDiT:
         self._rope: Optional[torch.Tensor] = None
         self._pos_key = None
         self._pos: Optional[torch.Tensor] = None
+        # CUDA-graph replay of the (timestep-invariant) forward: one captured graph per input shape
+        self.use_cuda_graphs = os.environ.get("DK_CUDA_GRAPHS", "1") != "0"
+        self._graphs: Dict[tuple, tuple] = {}
 
     # ------------------------------------------------------------------------------------------ weight packing
     def _pack(self, P: Dict[str, torch.Tensor]):
@@ -168,7 +172,10 @@ class MMDiT:
                         bias=self.t2[1])
         cin = ops.silu_add(y, tvec)                                                    # (n_t * B, h)
         self._mod_all = ops.gemm(cin, self.w_mod, bias=self.b_mod)                    # (n_t * B, mod_total)
-        self._mod_cur = torch.empty((B, self.mod_total), dtype=self.dtype, device=self.device)
+        if self._mod_cur is None or self._mod_batch != B:
+            # persistent buffer: captured graphs read the current step's modulation rows from this address
+            self._mod_cur = torch.empty((B, self.mod_total), dtype=self.dtype, device=self.device)
+            self._graphs = {}
         self._mod_batch = B
         self._mod_index = {}
         for i, t in enumerate(ts):
@@ -176,7 +183,7 @@ class MMDiT:
         self._cur_t = None
 
     def clear_modulation_params_cache(self):
-        self._mod_index, self._mod_all, self._mod_cur = {}, None, None
+        self._mod_index, self._mod_all = {}, None
 
     def select_timestep(self, timestep: float):
         """Make `timestep`'s modulation rows current (one D2D copy; keeps the forward timestep-invariant)."""
@@ -291,7 +298,29 @@ class MMDiT:
                 self.select_timestep(tval)
         if self._mod_cur is None or self._mod_batch != B:
             raise DkError(f"modulation cache holds batch {self._mod_batch}, forward got batch {B}")
+        if not self.use_cuda_graphs:
+            return self._forward_impl(x, text, B, H, W, Cl, T)
+        key = (B, H, W, Cl, T)
+        entry = self._graphs.get(key)
+        if entry is None:
+            sx, st = x.clone(), text.clone()
+            self._forward_impl(sx, st, B, H, W, Cl, T)            # eager warm-up: workspaces, tables, func attributes
+            torch.cuda.current_stream().synchronize()
+            n0 = ops.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                so = self._forward_impl(sx, st, B, H, W, Cl, T)
+            entry = (graph, sx, st, so, ops.launch_count() - n0)
+            self._graphs[key] = entry
+        graph, sx, st, so, n_launch = entry
+        sx.copy_(x)
+        st.copy_(text)
+        graph.replay()
+        ops.note_graph_launches(n_launch)
+        return so
 
+    def _forward_impl(self, x, text, B, H, W, Cl, T):
+        c = self.config
         hp, wp = H // c.patch_size, W // c.patch_size
         N = hp * wp
         S = N + T

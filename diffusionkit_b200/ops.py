@@ -27,8 +27,17 @@ def ctx(device: Optional[int] = None) -> Context:
     return c
 
 
+_graph_launches = 0
+
+
+def note_graph_launches(n: int):
+    """kernels replayed from a captured CUDA graph (the C-side counter only sees the capture pass)"""
+    global _graph_launches
+    _graph_launches += n
+
+
 def launch_count() -> int:
-    return sum(c.launches for c in _ctx.values())
+    return sum(c.launches for c in _ctx.values()) + _graph_launches
 
 
 def _chk16(t: torch.Tensor, name: str):
