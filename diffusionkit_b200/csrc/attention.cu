@@ -479,9 +479,9 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         const int st_n = (st + 1 == KS) ? 0 : st + 1;
         const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
         const bool more = j + 1 < n_tiles;
-        mbar_wait_spin_warp(&v_full[st], par);
-        mbar_wait_spin_warp(&p_full[0], j & 1);
-        if (more) mbar_wait_spin_warp(&k_full[st_n], par_n);
+        mbar_wait(&v_full[st], par);
+        mbar_wait(&p_full[0], j & 1);
+        if (more) mbar_wait(&k_full[st_n], par_n);
         tc_fence_after();
         if (elect_one_sync()) {
           issue_pv(0, st, j == 0);
@@ -489,7 +489,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
           if (more) issue_qk(0, st_n);
         }
         __syncwarp();
-        mbar_wait_spin_warp(&p_full[1], j & 1);
+        mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
         if (elect_one_sync()) {
           issue_pv(1, st, j == 0);
@@ -519,7 +519,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     const float sl2 = p.scale_log2;
 
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait_spin_warp(&s_full[w], j & 1);
+      mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
       if (p.debug >= 3) {   // timing experiment: pure barrier round trip, no TMEM traffic
         tc_fence_before();
@@ -621,7 +621,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     }
 
     // epilogue: O_w / l -> global
-    mbar_wait_spin_warp(&o_full[w], 0);
+    mbar_wait(&o_full[w], 0);
     tc_fence_after();
     const int s_idx = q0 + w * ATT_BQ + r;
     const bool row_ok = s_idx < p.S;

@@ -73,8 +73,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Latency-critical wait: non-blocking test_wait in a tight spin (try_wait parks the thread in hardware and its wake-up
-// after the phase completes was measured to cost on the order of a microsecond in dependent producer/consumer chains).
+// Non-blocking test_wait spin.  Measured SLOWER than the hardware-suspended try_wait for attention's s_full / p_full
+// ping-pong (476 vs 531-845 TFLOP/s at the C4 shape): the spinning lanes compete with the issuing warps.  Kept for
+// experiments only.
 __device__ __forceinline__ uint32_t mbar_test_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
