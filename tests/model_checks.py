@@ -192,6 +192,48 @@ def check_pipeline_errors():
     return {}
 
 
+def check_full_size_flux_properties():
+    """FLUX.1-schnell at its real width/depth (11.9 B synthetic parameters), 512x512, 4 steps: size-independent
+    properties the oracle cannot check in seconds — determinism (no atomics on the path), batch independence
+    (image i of a batch == the same seed/prompt alone; the property batch sharding across GPUs relies on), finiteness."""
+    pipe = dk.FluxPipeline(w16=True, a16=True, shift=1.0, model_version="argmaxinc/mlx-FLUX.1-schnell",
+                           load_decoder=False)
+    cond, pooled = pipe.synthetic_text_embeddings(n_images=2)
+    kw = dict(num_steps=4, cfg_weight=0.0, latent_size=(64, 64))
+    a, _ = pipe.denoise_latents(cond, pooled, seed=[5, 6], **kw)
+    b, _ = pipe.denoise_latents(cond, pooled, seed=[5, 6], **kw)
+    assert torch.equal(a, b), "denoise loop is not deterministic"
+    solo, _ = pipe.denoise_latents(cond[1:2], pooled[1:2], seed=6, **kw)
+    assert bool(torch.isfinite(a).all())
+    r = rel_l2(a[1:2], solo)
+    assert r <= 1e-5, f"batch composition changed image 1: rel_l2 {r:.3e}"
+    # statistics of a 4-step latent stay in a sane range for unit-variance synthetic inputs
+    return {"batch_vs_solo_rel_l2": r, "latent_abs_mean": float(a.abs().mean()), "latent_abs_max": float(a.abs().max())}
+
+
+def check_full_size_vae_properties():
+    """VAE decode at 1024x1024: batch independence, determinism, range."""
+    vp = init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=8, dtype=torch.bfloat16, device=DEV)
+    dec = dk.VAEDecoder(vp)
+    g = torch.Generator().manual_seed(2)
+    z = torch.randn((2, 128, 128, 16), generator=g).to(torch.bfloat16).to(DEV)
+
+    def run(zz):
+        raw = dec(zz)
+        Bo, Ho, Wo, _ = raw.shape
+        padded = raw.as_strided((Bo, Ho, Wo, raw.stride(2)), (raw.stride(0), raw.stride(1), raw.stride(2), 1))
+        return ops.image_post(padded)
+
+    f2, u2 = run(z)
+    f2b, _ = run(z)
+    assert torch.equal(f2, f2b), "VAE decode is not deterministic"
+    f1, u1 = run(z[1:2].contiguous())
+    assert f2.shape == (2, 1024, 1024, 3) and float(f2.min()) >= 0.0 and float(f2.max()) <= 1.0
+    d = (u2[1:2].int() - u1.int()).abs()
+    assert int(d.max()) == 0, f"batch composition changed image 1 by {int(d.max())} uint8 levels"
+    return {"u8_max_diff_batch_vs_solo": int(d.max()), "mean": float(f2.mean())}
+
+
 ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
               check_vae_decode_tiny, check_vae_decode_batch_fp16, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
-              check_pipeline_errors]
+              check_pipeline_errors, check_full_size_flux_properties, check_full_size_vae_properties]
