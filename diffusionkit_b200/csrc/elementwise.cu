@@ -359,7 +359,7 @@ static inline int gn_chunks(int HW) {
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C, int G, int chunks) {
-  extern __shared__ float sm[];  // [2*C]
+  extern __shared__ float sm[];  // [2*C] channel totals + 2 x [GN_THREADS*8] staging
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int per = (HW + chunks - 1) / chunks;
   const int p0 = chunk * per;
@@ -395,14 +395,26 @@ groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, i
       }
     }
   }
-  for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
-  __syncthreads();
+  // deterministic in-block reduction (fixed summation order, no atomics): stage every thread's 8 channel sums as
+  // [pixel slot][channel], then one thread per channel folds the pixel slots in order
+  float* st_s = sm + 2 * C;                    // [pix_per_iter][C]
+  float* st_q = st_s + GN_THREADS * 8;         // [pix_per_iter][C]
   if (my_pix < pix_per_iter) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[my_vec * 8 + j], s[j]);
-      atomicAdd(&sm[C + my_vec * 8 + j], q[j]);
+      st_s[my_pix * C + my_vec * 8 + j] = s[j];
+      st_q[my_pix * C + my_vec * 8 + j] = q[j];
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+    float ts = 0.f, tq = 0.f;
+    for (int pp = 0; pp < pix_per_iter; ++pp) {
+      ts += st_s[pp * C + c];
+      tq += st_q[pp * C + c];
+    }
+    sm[c] = ts;
+    sm[C + c] = tq;
   }
   __syncthreads();
   const int cpg = C / G;
@@ -757,7 +769,7 @@ extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* 
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int chunks = gn_chunks(HW);
   dim3 grid(chunks, B);
-  DK_DISPATCH(dtype, (groupnorm_partial_kernel<T><<<grid, GN_THREADS, 2 * C * sizeof(float), stream>>>(
+  DK_DISPATCH(dtype, (groupnorm_partial_kernel<T><<<grid, GN_THREADS, (2 * C + 2 * GN_THREADS * 8) * sizeof(float), stream>>>(
                          static_cast<const T*>(x), ws, HW, C, G, chunks)));
   DK_LAUNCH_CHECK(ctx);
   groupnorm_finalize_kernel<<<(B * G + 127) / 128, 128, 0, stream>>>(
