@@ -97,6 +97,28 @@ def main():
         fl = 2.0 * B * H * W * Cout * 9 * Cin
         res[name] = {"ms": med * 1e3, "tflops": fl / med / 1e12}
         del xx, ww, oo
+    # VAE HBM-bound kernels at the 1024x1024 level (B=1): GroupNorm statistics / apply, nearest upsample, image post
+    for name, (H, C) in {"512x512x256": (512, 256), "1024x1024x128": (1024, 128)}.items():
+        xx = torch.randn((1, H, H, C), device=DEV, dtype=dt)
+        gam = torch.ones(C, device=DEV, dtype=dt)
+        bet = torch.zeros(C, device=DEV, dtype=dt)
+        ws = torch.empty(1 << 20, device=DEV, dtype=torch.float32)
+        yy = torch.empty_like(xx)
+        med, _ = timeit(lambda: ops.groupnorm_stats(xx, 32, 1e-5, ws=ws), iters=5)
+        res["groupnorm_stats " + name] = {"ms": med * 1e3, "gbs": xx.numel() * 2 / med / 1e9}
+        st = ops.groupnorm_stats(xx, 32, 1e-5, ws=ws)
+        med, _ = timeit(lambda: ops.groupnorm_apply(xx, st, gam, bet, 32, True, out=yy), iters=5)
+        res["groupnorm_apply+silu " + name] = {"ms": med * 1e3, "gbs": 2 * xx.numel() * 2 / med / 1e9}
+        del xx, yy
+    xs = torch.randn((1, 512, 512, 256), device=DEV, dtype=dt)
+    ys = torch.empty((1, 1024, 1024, 256), device=DEV, dtype=dt)
+    med, _ = timeit(lambda: ops.upsample_nearest2x(xs, out=ys), iters=5)
+    res["upsample2x 512->1024 x256"] = {"ms": med * 1e3, "gbs": (xs.numel() + ys.numel()) * 2 / med / 1e9}
+    del xs, ys
+    sc = torch.randn((16384, 16384), device=DEV, dtype=dt)
+    med, _ = timeit(lambda: ops.softmax_rows(sc, 0.044), iters=5)
+    res["softmax_rows 16384x16384"] = {"ms": med * 1e3, "gbs": 2 * sc.numel() * 2 / med / 1e9}
+    del sc
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "bench_kernels.json"), "w") as f:
         json.dump(res, f, indent=1)
