@@ -374,15 +374,23 @@ groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, i
   if (my_pix < pix_per_iter) {
     const T* base = x + static_cast<long long>(b) * HW * C + my_vec * 8;
     int p = p0 + my_pix;
-    // two independent loads in flight per thread
-    for (; p + pix_per_iter < p1; p += 2 * pix_per_iter) {
-      float v0[8], v1[8];
-      load8(base + static_cast<long long>(p) * C, v0);
-      load8(base + static_cast<long long>(p + pix_per_iter) * C, v1);
+    // four independent 128-bit loads in flight per thread (HBM latency hiding)
+    for (; p + 3 * pix_per_iter < p1; p += 4 * pix_per_iter) {
+      uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += v0[j] + v1[j];
-        q[j] += v0[j] * v0[j] + v1[j] * v1[j];
+      for (int k = 0; k < 4; ++k)
+        u[k] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(p + k * pix_per_iter) * C);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = Half16<T>::unpack(w[i]);
+          s[2 * i] += f.x;
+          s[2 * i + 1] += f.y;
+          q[2 * i] += f.x * f.x;
+          q[2 * i + 1] += f.y * f.y;
+        }
       }
     }
     for (; p < p1; p += pix_per_iter) {
@@ -471,7 +479,34 @@ groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* 
     }
   }
   const long long img = static_cast<long long>(b) * HW * C + my_vec * 8;
-  for (int p = blockIdx.x * pix_per_iter + my_pix; p < HW; p += gridDim.x * pix_per_iter) {
+  const int step = gridDim.x * pix_per_iter;
+  int p = blockIdx.x * pix_per_iter + my_pix;
+  // four pixels per iteration: all loads issued before the first use
+  for (; p + 3 * step < HW; p += 4 * step) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      u[k] = *reinterpret_cast<const uint4*>(x + img + static_cast<long long>(p + k * step) * C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = Half16<T>::unpack(w[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float o = fmaf(v[j], sc[j], sh[j]);
+        if (silu) o = silu_f(round16<T>(o));
+        v[j] = o;
+      }
+      store8(y + img + static_cast<long long>(p + k * step) * C, v);
+    }
+  }
+  for (; p < HW; p += step) {
     float v[8];
     load8(x + img + static_cast<long long>(p) * C, v);
 #pragma unroll
