@@ -335,6 +335,314 @@ struct Att2Cfg {
   static constexpr int TMEM_O = 256;   // + 128 * w
 };
 
+// ---- v2a: the first v2 implementation (single-lane issue loops, one TMEM pass, all-MUFU exponentials), kept
+// ---- selectable (DK_ATTENTION_IMPL=2a) for same-box A/B measurements against the current kernel
+template <typename T, int D>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attention_fwd_v2a_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+  using H16 = Half16<T>;
+  using Cfg = Att2Cfg<D>;
+  constexpr int KS = Cfg::KS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;             // [KS]
+  uint64_t* k_empty = k_full + KS;         // [KS]
+  uint64_t* v_full = k_empty + KS;         // [KS]
+  uint64_t* v_empty = v_full + KS;         // [KS]
+  uint64_t* s_full = v_empty + KS;         // [2]  QK_w(j) retired
+  uint64_t* p_full = s_full + 2;           // [2]  softmax_w(j) published P_w(j) (128 arrivals)
+  uint64_t* o_full = p_full + 2;           // [2]  PV_w(n-1) retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int h = p.heads * D;
+  const int n_tiles = (p.S + ATT_BKV - 1) / ATT_BKV;
+  const int row_base = b * p.S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // producer warpgroup: give its registers to the softmax warpgroups
+    setmaxnreg_dec<112>();
+    if (warp == 0 && lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a)
+          tma_load_2d(sQ + w * Cfg::TILE_BYTES + a * 16384, &tmQKV, q_full, head * D + a * 64,
+                      row_base + q0 + w * ATT_BQ);
+      int st = 0;
+      uint32_t par = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int kv_row = row_base + j * ATT_BKV;
+        mbar_wait(&k_empty[st], par ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a)
+          tma_load_2d(sK + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &k_full[st], h + head * D + a * 64, kv_row);
+        mbar_wait(&v_empty[st], par ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < D / 64; ++a)
+          tma_load_2d(sV + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &v_full[st], 2 * h + head * D + a * 64, kv_row);
+        if (++st == KS) {
+          st = 0;
+          par ^= 1;
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc_qk = make_idesc_f16(ATT_BQ, ATT_BKV, H16::is_bf16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(ATT_BQ, D, H16::is_bf16, false, true);
+      auto issue_qk = [&](int w, int st) {
+        const uint32_t q_addr = smem_u32(sQ + w * Cfg::TILE_BYTES);
+        const uint32_t k_addr = smem_u32(sK + st * Cfg::TILE_BYTES);
+        const uint32_t d_tmem = tmem_base + Cfg::TMEM_S + w * 128;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          umma_ss(d_tmem, make_smem_desc_sw128(q_addr + off, 0, 1024), make_smem_desc_sw128(k_addr + off, 0, 1024),
+                  idesc_qk, k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[w]);
+      };
+      auto issue_pv = [&](int w, int st, bool first) {
+        const uint32_t v_addr = smem_u32(sV + st * Cfg::TILE_BYTES);
+        const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + w * 128;   // P_w: 16-bit pairs in S_w's first 64 columns
+        const uint32_t d_tmem = tmem_base + Cfg::TMEM_O + w * 128;
+#pragma unroll
+        for (int k = 0; k < ATT_BKV / 16; ++k)
+          umma_ts(d_tmem, p_tmem + k * 8, make_smem_desc_sw128(v_addr + k * 2048, 16384, 1024), idesc_pv,
+                  (!first || k != 0) ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&k_empty[0]);
+      int st = 0;
+      uint32_t par = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st_n = (st + 1 == KS) ? 0 : st + 1;
+        const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
+        const bool more = j + 1 < n_tiles;
+        mbar_wait(&v_full[st], par);
+        mbar_wait(&p_full[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, st, j == 0);
+        if (!more) umma_commit(&o_full[0]);
+        if (more) {
+          mbar_wait(&k_full[st_n], par_n);
+          tc_fence_after();
+          issue_qk(0, st_n);
+        }
+        mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, st, j == 0);
+        umma_commit(&v_empty[st]);
+        if (!more) umma_commit(&o_full[1]);
+        if (more) {
+          issue_qk(1, st_n);
+          umma_commit(&k_empty[st_n]);
+        }
+        st = st_n;
+        par = par_n;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax warpgroups (w = 0: A, 1: B)
+    setmaxnreg_inc<192>();
+    const int w = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + Cfg::TMEM_S + w * 128;
+    const uint32_t t_o = t_lane + Cfg::TMEM_O + w * 128;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    const float sl2 = p.scale_log2;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[w], j & 1);
+      tc_fence_after();
+      const int kv_valid = p.S - j * ATT_BKV;   // keys beyond the sequence end exist only on the tail tile
+
+      // pass 1 over the S row: running max of the raw scores (the positive scale commutes with max).
+      // TMEM reads are cheap (16 TB/s per SM), so the row is read twice instead of being held in 128 registers.
+      float mx;
+      {
+        uint32_t sr[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_s + c * 32, sr[c]);
+        tmem_ld_wait();
+        if (kv_valid < ATT_BKV) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[2][i]));
+          mx3 = fmaxf(mx3, __uint_as_float(sr[3][i]));
+        }
+        mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * sl2;
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const bool need = (m_new - m_run) > 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = ex2_approx(m_run - m_new);
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+          // PV_w(j-1) was issued before QK_w(j), whose completion s_full signalled: O_w is quiescent
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_o + c * 32, o);
+          }
+        }
+      }
+      // pass 2: P = exp2(s * sl2 - m_run), packed two 16-bit values per 32-bit TMEM column (key 2i in the low half),
+      // written over the first 64 columns of this warpgroup's own S accumulator
+      float ls0 = 0.f, ls1 = 0.f;
+      uint32_t pk[2][32];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sa[32], sb[32];
+        tmem_ld_32x32(t_s + half * 64, sa);
+        tmem_ld_32x32(t_s + half * 64 + 32, sb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a0 = __uint_as_float(sa[2 * i]), a1 = __uint_as_float(sa[2 * i + 1]);
+          float b0 = __uint_as_float(sb[2 * i]), b1 = __uint_as_float(sb[2 * i + 1]);
+          if (kv_valid < ATT_BKV) {
+            const int k0 = half * 64 + 2 * i;
+            if (k0 >= kv_valid) a0 = -INFINITY;
+            if (k0 + 1 >= kv_valid) a1 = -INFINITY;
+            if (k0 + 32 >= kv_valid) b0 = -INFINITY;
+            if (k0 + 33 >= kv_valid) b1 = -INFINITY;
+          }
+          const float e0 = ex2_approx(fmaf(a0, sl2, -m_run));
+          const float e1 = ex2_approx(fmaf(a1, sl2, -m_run));
+          const float f0 = ex2_approx(fmaf(b0, sl2, -m_run));
+          const float f1 = ex2_approx(fmaf(b1, sl2, -m_run));
+          ls0 += e0 + f0;
+          ls1 += e1 + f1;
+          pk[half][i] = H16::pack(e0, e1);
+          pk[half][16 + i] = H16::pack(f0, f1);
+        }
+      }
+      // all reads of S_w by this thread are complete (wait::ld above) before P overwrites its first 64 columns
+      tmem_st_32x32(t_s, pk[0]);
+      tmem_st_32x32(t_s + 32, pk[1]);
+      l_run += ls0 + ls1;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[w]);
+    }
+
+    // epilogue: O_w / l -> global
+    mbar_wait(&o_full[w], 0);
+    tc_fence_after();
+    const int s_idx = q0 + w * ATT_BQ + r;
+    const bool row_ok = s_idx < p.S;
+    T* dst = nullptr;
+    if (row_ok) {
+      if (s_idx < p.split)
+        dst = reinterpret_cast<T*>(p.out0) + (static_cast<long long>(b) * p.split + s_idx) * p.ld0 + head * D;
+      else
+        dst = reinterpret_cast<T*>(p.out1) +
+              (static_cast<long long>(b) * (p.S - p.split) + (s_idx - p.split)) * p.ld1 + head * D;
+    }
+    const float inv_l = 1.0f / l_run;
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_o + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = H16::pack(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
+          pk.y = H16::pack(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
+          pk.z = H16::pack(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
+          pk.w = H16::pack(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+template <typename T, int D>
+static int launch_attention_v2a(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+  using Cfg = Att2Cfg<D>;
+  auto kern = attention_fwd_v2a_kernel<T, D>;
+  static bool configured = false;
+  if (!configured) {
+    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid(dk_ceil_div(p.S, 2 * ATT_BQ), p.heads, p.B);
+  kern<<<grid, ATT2_THREADS, Cfg::SMEM_BYTES, stream>>>(tm, p);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 // POLY: how many of every four exponentials are evaluated on the FMA pipe (ex2_poly) instead of MUFU.EX2
 template <typename T, int D, int POLY>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
@@ -742,6 +1050,18 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
   p.ld1 = ld1;
   // DK_ATT_POLY (0..2, default 1): share of the softmax exponentials evaluated on the FMA pipe (tuning knob)
 // DK_ATTENTION_V1=1 selects the single-Q-tile kernel with P staged through shared memory (kept for A/B checks)
+  static const bool use_v2a = [] {
+    const char* e = getenv("DK_ATTENTION_IMPL");
+    return e != nullptr && e[0] == '2' && e[1] == 'a';
+  }();
+  if (use_v2a) {
+    if (dtype == DK_BF16) {
+      if (d == 128) return launch_attention_v2a<__nv_bfloat16, 128>(ctx, tm, p, stream);
+      return launch_attention_v2a<__nv_bfloat16, 64>(ctx, tm, p, stream);
+    }
+    if (d == 128) return launch_attention_v2a<__half, 128>(ctx, tm, p, stream);
+    return launch_attention_v2a<__half, 64>(ctx, tm, p, stream);
+  }
   static const bool use_v1 = [] {
     const char* e = getenv("DK_ATTENTION_V1");
     return e != nullptr && e[0] == '1';

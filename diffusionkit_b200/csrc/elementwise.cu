@@ -437,22 +437,32 @@ groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, i
     dst[1] = tq;
   }
 }
+// one warp per (b, g): lanes stride over the chunk partials (fixed lane -> chunk assignment, fixed shuffle tree:
+// deterministic), accumulation in double
 __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int B, int G,
                                           int chunks, double count, float eps) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (idx >= B * G) return;
   const int b = idx / G, g = idx % G;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < chunks; ++c) {
-    const float* p = partial + ((static_cast<long long>(b) * chunks + c) * G + g) * 2;
-    s += p[0];
-    q += p[1];
+  for (int c = lane; c < chunks; c += 32) {
+    const float2 p = *reinterpret_cast<const float2*>(partial + ((static_cast<long long>(b) * chunks + c) * G + g) * 2);
+    s += p.x;
+    q += p.y;
   }
-  const double mean = s / count;
-  double var = q / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  stats[idx * 2] = static_cast<float>(mean);
-  stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane == 0) {
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[idx * 2] = static_cast<float>(mean);
+    stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
 }
 template <typename T>
 __global__ void __launch_bounds__(GN_THREADS)
@@ -807,7 +817,7 @@ extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* 
   DK_DISPATCH(dtype, (groupnorm_partial_kernel<T><<<grid, GN_THREADS, (2 * C + 2 * GN_THREADS * 8) * sizeof(float), stream>>>(
                          static_cast<const T*>(x), ws, HW, C, G, chunks)));
   DK_LAUNCH_CHECK(ctx);
-  groupnorm_finalize_kernel<<<(B * G + 127) / 128, 128, 0, stream>>>(
+  groupnorm_finalize_kernel<<<(B * G * 32 + 127) / 128, 128, 0, stream>>>(
       ws, stats, B, G, chunks, static_cast<double>(HW) * (C / G), eps);
   DK_LAUNCH_CHECK(ctx);
   return 0;
