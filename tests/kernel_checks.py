@@ -467,6 +467,57 @@ def check_softmax_image_post():
     return out
 
 
+def check_edge_cases():
+    """smallest / most ragged shapes every kernel accepts"""
+    _setup()
+    out = {}
+    out["gemm_1x8x8"] = _gemm_case(1, 8, 8, torch.bfloat16, bias=True, name="gemm_1x8x8")
+    out["gemm_129x72x24"] = _gemm_case(129, 72, 24, torch.float16, bias=True, act=ACT_SILU, name="gemm_129x72x24")
+    out["att_S1"] = _attention_case(2, 1, 2, 128, torch.bfloat16, name="att_S1")
+    out["att_S129"] = _attention_case(1, 129, 1, 64, torch.float16, name="att_S129")
+    out["att_S257_split1"] = _attention_case(1, 257, 2, 128, torch.bfloat16, split=1, name="att_S257")
+    out["conv_1x1"] = _conv_case(1, 1, 1, 64, 8, torch.bfloat16, name="conv_1x1")
+    out["conv_3x5"] = _conv_case(2, 3, 5, 64, 24, torch.bfloat16, res=True, name="conv_3x5")
+    x = _rand((3, 64), torch.bfloat16, 2.0)
+    mod = _rand((3, 128), torch.bfloat16, 0.3)
+    ref = torch.nn.functional.layer_norm(x.float(), (64,), eps=1e-6) * (1 + mod[:, 64:].float()) + mod[:, :64].float()
+    out["ln_h64"] = _assert_close("ln_h64", ops.ln_modulate(x, mod[:, :64], mod[:, 64:], 1, 1e-6), ref, 4e-3)
+    g = _rand((1, 1, 1, 64), torch.bfloat16)
+    st = ops.groupnorm_stats(g, 32, 1e-5)
+    assert bool(torch.isfinite(st).all())
+    return out
+
+
+def check_error_paths():
+    """invalid arguments are refused with an error code + message (no launch, no crash)"""
+    _setup()
+    from diffusionkit_b200._lib import DkError
+
+    A = _rand((16, 64), torch.bfloat16)
+    W = _rand((16, 64), torch.bfloat16)
+    cases = {
+        "N not multiple of 8": lambda: ops.gemm(A, _rand((12, 64), torch.bfloat16)),
+        "K not multiple of 8": lambda: ops.gemm(_rand((16, 12), torch.bfloat16), _rand((16, 12), torch.bfloat16)),
+        "misaligned A": lambda: ops.gemm(_rand((16, 72), torch.bfloat16)[:, 4:68], W),
+        "head dim 96": lambda: ops.attention(_rand((8, 3 * 96), torch.bfloat16), 1, 8, 1, 96,
+                                             torch.empty((8, 96), dtype=torch.bfloat16, device=DEV)),
+        "conv Cin 48": lambda: ops.conv3x3(_rand((1, 4, 4, 48), torch.bfloat16), _rand((8, 3, 3, 48), torch.bfloat16)),
+        "fp32 input": lambda: ops.gemm(A.float(), W.float()),
+        "cpu tensor": lambda: ops.gemm(A.cpu(), W.cpu()),
+        "ln h too wide": lambda: ops.ln_modulate(_rand((2, 8192), torch.bfloat16), _rand((2, 8192), torch.bfloat16),
+                                                 _rand((2, 8192), torch.bfloat16), 1),
+    }
+    for name, fn in cases.items():
+        try:
+            fn()
+        except DkError as e:
+            assert len(str(e)) > 0
+            continue
+        raise AssertionError(f"{name}: accepted")
+    # the context is still healthy afterwards
+    return {"after": _gemm_case(128, 128, 64, torch.bfloat16, name="gemm_after_errors")}
+
+
 ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
     check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
@@ -474,5 +525,5 @@ ALL_CHECKS = [
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
     check_attention_v1_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
-    check_softmax_image_post,
+    check_softmax_image_post, check_edge_cases, check_error_paths,
 ]
