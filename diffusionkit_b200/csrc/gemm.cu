@@ -334,6 +334,10 @@ extern "C" int dk_gemm(dk_ctx* ctx, const dk_gemm_args* a, void* stream_) {
   e.res_batch_rows = a->rows_per_batch > 0 ? a->res_batch_rows : a->M;
   e.res_row_off = a->res_row_off;
   e.act = a->act;
+  {
+    static const int dbg = [] { const char* v = getenv("DK_GEMM_EPI_DEBUG"); return v ? atoi(v) : 0; }();
+    e.debug = dbg;
+  }
   e.qk_qw = a->qk_q_weight;
   e.qk_kw = a->qk_k_weight;
   e.qk_rope = a->qk_rope;

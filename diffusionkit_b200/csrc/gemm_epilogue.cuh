@@ -24,6 +24,7 @@ struct GemmEpi {
   int out_batch_rows, out_row_off;
   int res_batch_rows, res_row_off;
   int act;
+  int debug;  // timing experiments only (DK_GEMM_EPI_DEBUG): 1 = skip the global stores, 2 = skip everything after TMEM->regs
   // fused QK-RMSNorm + RoPE on the q and k thirds of a packed QKV projection (columns [0, 2*qk_h)); qk_d == 0 disables
   const void* qk_qw;   // [d] RMSNorm weight of q (or NULL: no norm)
   const void* qk_kw;   // [d]
@@ -100,7 +101,7 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmShape& s, const Ge
       tmem_ld_32x32(t_row + (hc + c) * 32, r);
       tmem_ld_wait();
       if (hc + c == NCH - 1) release_acc();
-      if (!row_ok) continue;
+      if (!row_ok || e.debug >= 2) continue;
       const int n0 = n_half0 + (hc + c) * 32;
       const int dcol0 = head_col0 + c * 32;  // column inside the head
 #pragma unroll
@@ -147,7 +148,7 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmShape& s, const Ge
         o.y = H16::pack(v[2], v[3]);
         o.z = H16::pack(v[4], v[5]);
         o.w = H16::pack(v[6], v[7]);
-        __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: do not displace A / W tiles in L2
+        if (e.debug == 0) __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: keep A / W tiles in L2
       }
     }
   }
@@ -161,7 +162,7 @@ for (int chunk = 0; chunk < NCH; ++chunk) {
   tmem_ld_wait();
   if (chunk == NCH - 1) release_acc();
   const int n0 = n_half0 + chunk * 32;
-  if (!row_ok) continue;
+  if (!row_ok || e.debug >= 2) continue;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int n = n0 + j * 8;
@@ -211,7 +212,7 @@ for (int chunk = 0; chunk < NCH; ++chunk) {
     o.y = H16::pack(v[2], v[3]);
     o.z = H16::pack(v[4], v[5]);
     o.w = H16::pack(v[6], v[7]);
-    __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: do not displace A / W tiles in L2
+    if (e.debug == 0) __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: keep A / W tiles in L2
   }
 }
 }
