@@ -41,6 +41,20 @@ struct ConvGeom {
 };
 
 
+// 16 finished 16-bit values of one row -> global.  One 256-bit store (a full 32-byte sector per thread) when the
+// address allows it: with 128-bit stores every sector is written by two separate requests and the store path cost the
+// pair GEMM 6 % of its sustained (power-capped) throughput.
+__device__ __forceinline__ void store_row16(void* dst, const uint32_t (&w)[8], bool wide) {
+  if (wide) {
+    asm volatile("st.global.cs.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]), "r"(w[1]),
+                 "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+  } else {
+    __stcs(reinterpret_cast<uint4*>(dst), make_uint4(w[0], w[1], w[2], w[3]));
+    __stcs(reinterpret_cast<uint4*>(dst) + 1, make_uint4(w[4], w[5], w[6], w[7]));
+  }
+}
+
 // Drains NCH 32-column chunks of one accumulator row (this thread = one tile row; t_row = TMEM address of the row's
 // first column owned by this warp) and stores the finished 16-bit values.  `release()` is called exactly once, right
 // after the last TMEM read, so the accumulator can be handed back to the MMA warp before the stores retire.
@@ -104,6 +118,7 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmShape& s, const Ge
       if (!row_ok || e.debug >= 2) continue;
       const int n0 = n_half0 + (hc + c) * 32;
       const int dcol0 = head_col0 + c * 32;  // column inside the head
+      uint32_t w16[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int n = n0 + j * 8;
@@ -143,12 +158,12 @@ __device__ __forceinline__ void gemm_epilogue_drain(const GemmShape& s, const Ge
             v[4 * i + 3] = b0 * cs.w + b1 * cs.z;
           }
         }
-        uint4 o;
-        o.x = H16::pack(v[0], v[1]);
-        o.y = H16::pack(v[2], v[3]);
-        o.z = H16::pack(v[4], v[5]);
-        o.w = H16::pack(v[6], v[7]);
-        if (e.debug == 0) __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: keep A / W tiles in L2
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w16[(j & 1) * 4 + i] = H16::pack(v[2 * i], v[2 * i + 1]);
+        if ((j & 1) && e.debug == 0) {
+          T* dst = out + orow * e.ldc + (n - 8);
+          store_row16(dst, w16, (reinterpret_cast<uintptr_t>(dst) & 31u) == 0);
+        }
       }
     }
   }
@@ -164,55 +179,66 @@ for (int chunk = 0; chunk < NCH; ++chunk) {
   const int n0 = n_half0 + chunk * 32;
   if (!row_ok || e.debug >= 2) continue;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int n = n0 + j * 8;
-    if (n >= s.N) break;
-    float v[8];
+  for (int j16 = 0; j16 < 2; ++j16) {
+    const int nb = n0 + j16 * 16;
+    if (nb >= s.N) break;
+    uint32_t w[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
-    if (bias != nullptr) {
-      const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n);
-      const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int hh = 0; hh < 2; ++hh) {
+      const int j = j16 * 2 + hh;
+      const int n = n0 + j * 8;
+      float v[8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = H16::unpack(bw[i]);
-        v[2 * i] += f.x;
-        v[2 * i + 1] += f.y;
+      for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+      if (n < s.N) {
+        if (bias != nullptr) {
+          const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n);
+          const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = H16::unpack(bw[i]);
+            v[2 * i] += f.x;
+            v[2 * i + 1] += f.y;
+          }
+        }
+        if (e.act == DK_ACT_GELU_ERF) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        } else if (e.act == DK_ACT_SILU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+        }
+        if (gate != nullptr) {
+          const uint4 g4 = *reinterpret_cast<const uint4*>(gate + static_cast<long long>(batch) * e.gate_ld + n);
+          const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = H16::unpack(gw[i]);
+            v[2 * i] *= f.x;
+            v[2 * i + 1] *= f.y;
+          }
+        }
+        if (res != nullptr) {
+          const uint4 r4 = *reinterpret_cast<const uint4*>(res + rrow * e.ldres + n);
+          const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = H16::unpack(rw[i]);
+            v[2 * i] += f.x;
+            v[2 * i + 1] += f.y;
+          }
+        }
       }
-    }
-    if (e.act == DK_ACT_GELU_ERF) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
-    } else if (e.act == DK_ACT_SILU) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+      for (int i = 0; i < 4; ++i) w[hh * 4 + i] = H16::pack(v[2 * i], v[2 * i + 1]);
     }
-    if (gate != nullptr) {
-      const uint4 g4 = *reinterpret_cast<const uint4*>(gate + static_cast<long long>(batch) * e.gate_ld + n);
-      const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = H16::unpack(gw[i]);
-        v[2 * i] *= f.x;
-        v[2 * i + 1] *= f.y;
-      }
+    if (e.debug != 0) continue;
+    T* dst = out + orow * e.ldc + nb;
+    if (nb + 16 <= s.N) {
+      store_row16(dst, w, (reinterpret_cast<uintptr_t>(dst) & 31u) == 0);
+    } else {
+      __stcs(reinterpret_cast<uint4*>(dst), make_uint4(w[0], w[1], w[2], w[3]));   // 8-column tail
     }
-    if (res != nullptr) {
-      const uint4 r4 = *reinterpret_cast<const uint4*>(res + rrow * e.ldres + n);
-      const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = H16::unpack(rw[i]);
-        v[2 * i] += f.x;
-        v[2 * i + 1] += f.y;
-      }
-    }
-    uint4 o;
-    o.x = H16::pack(v[0], v[1]);
-    o.y = H16::pack(v[2], v[3]);
-    o.z = H16::pack(v[4], v[5]);
-    o.w = H16::pack(v[6], v[7]);
-    if (e.debug == 0) __stcs(reinterpret_cast<uint4*>(out + orow * e.ldc + n), o);  // streaming: keep A / W tiles in L2
   }
 }
 }
