@@ -432,7 +432,12 @@ struct Half16<__half> {
 };
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
+// x * sigmoid(x) with ex2.approx + rcp.approx (the IEEE divide made the GroupNorm-apply kernel issue-bound)
+__device__ __forceinline__ float silu_f(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
+  return __fdividef(v, 1.0f + e);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

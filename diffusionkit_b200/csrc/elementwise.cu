@@ -529,20 +529,28 @@ groupnorm_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* 
   }
 }
 
+// nearest 2x: grid (output rows / rows-per-block, B); a thread owns one 128-bit channel vector of one output column
+// and walks output rows — no per-element divisions
 template <typename T>
-__global__ void upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
-  // y: [B, 2H, 2W, C]
-  const long long nvec = static_cast<long long>(B) * 4 * H * W * C / 8;
-  const int vpp = C / 8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int v = static_cast<int>(i % vpp);
-    const long long pix = i / vpp;
-    const int ox = static_cast<int>(pix % (2 * W));
-    const int oy = static_cast<int>((pix / (2 * W)) % (2 * H));
-    const int b = static_cast<int>(pix / (4LL * W * H));
-    *reinterpret_cast<uint4*>(y + pix * C + v * 8) =
-        *reinterpret_cast<const uint4*>(x + ((static_cast<long long>(b) * H + oy / 2) * W + ox / 2) * C + v * 8);
+__global__ void __launch_bounds__(256)
+upsample2x_kernel(const T* __restrict__ x, T* __restrict__ y, int H, int W, int C, int rows_per_block) {
+  const int b = blockIdx.y;
+  const int vpp = C / 8;                 // vectors per pixel
+  const int row_vecs = 2 * W * vpp;      // vectors per output row
+  const int oy0 = blockIdx.x * rows_per_block;
+  const int oy1 = min(2 * H, oy0 + rows_per_block);
+  const T* xin = x + static_cast<long long>(b) * H * W * C;
+  T* yout = y + static_cast<long long>(b) * 4 * H * W * C;
+  for (int v = threadIdx.x; v < row_vecs; v += blockDim.x) {
+    const int ox = v / vpp;
+    const int cv = v - ox * vpp;
+    const long long in_col = static_cast<long long>(ox >> 1) * C + cv * 8;
+    const long long out_col = static_cast<long long>(ox) * C + cv * 8;
+    for (int oy = oy0; oy < oy1; oy += 2) {   // rows oy, oy+1 replicate input row oy/2 (oy0 is even)
+      const uint4 u = *reinterpret_cast<const uint4*>(xin + static_cast<long long>(oy >> 1) * W * C + in_col);
+      __stcs(reinterpret_cast<uint4*>(yout + static_cast<long long>(oy) * 2 * W * C + out_col), u);
+      if (oy + 1 < oy1) __stcs(reinterpret_cast<uint4*>(yout + static_cast<long long>(oy + 1) * 2 * W * C + out_col), u);
+    }
   }
 }
 
@@ -848,9 +856,10 @@ extern "C" int dk_upsample_nearest2x(dk_ctx* ctx, int dtype, const void* x, void
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(C % 8 == 0, "dk_upsample_nearest2x: C must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const long long nvec = static_cast<long long>(B) * 4 * H * W * C / 8;
-  DK_DISPATCH(dtype, (upsample2x_kernel<T><<<grid_for(nvec, 256, ctx->sm_count), 256, 0, stream>>>(
-                         static_cast<const T*>(x), static_cast<T*>(y), B, H, W, C)));
+  const int rows_per_block = 2;   // even: both replicas of an input row are written by the same thread
+  dim3 grid((2 * H + rows_per_block - 1) / rows_per_block, B);
+  DK_DISPATCH(dtype, (upsample2x_kernel<T><<<grid, 256, 0, stream>>>(static_cast<const T*>(x), static_cast<T*>(y), H,
+                                                                       W, C, rows_per_block)));
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
