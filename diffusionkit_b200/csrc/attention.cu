@@ -788,7 +788,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
         const bool more = j + 1 < n_tiles;
         mbar_wait(&v_full[st], par);
-        mbar_wait(&p_full[0], j & 1);
+        if (p.debug < 4) mbar_wait(&p_full[0], j & 1);   // debug 4: tensor-side throughput without the softmax round trip
         if (more) mbar_wait(&k_full[st_n], par_n);
         tc_fence_after();
         if (elect_one_sync()) {
@@ -797,7 +797,7 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
           if (more) issue_qk(0, st_n);
         }
         __syncwarp();
-        mbar_wait(&p_full[1], j & 1);
+        if (p.debug < 4) mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
         if (elect_one_sync()) {
           issue_pv(1, st, j == 0);
