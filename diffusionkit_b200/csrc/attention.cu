@@ -969,6 +969,328 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   }
 }
 
+// ================================================================================================
+// v3: as v2 (two 128-row Q tiles per CTA, P kept in TMEM) but TWO softmax warpgroups per Q tile: warpgroup (w, hh)
+// owns the 64-key half hh of every row of tile w (both halves can reach the same TMEM lanes because lane access is
+// by warp %% 4).  Same-box measurements of v2: 1058 TFLOP/s with the softmax vs 1485 with the softmax work removed —
+// the single warp per scheduler could not hide the TMEM / MUFU latencies; v3 doubles the warps per scheduler and halves
+// the per-thread row.  The two halves of a row exchange their partial row max through shared memory (one named
+// barrier per tile) so that both use the same running max; partial row sums are combined once at the end.
+// ================================================================================================
+constexpr int ATT3_THREADS = 640;
+
+template <typename T, int D>
+__global__ void __launch_bounds__(ATT3_THREADS, 1)
+attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+  using H16 = Half16<T>;
+  using Cfg = Att2Cfg<D>;
+  constexpr int KS = Cfg::KS;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;             // [KS]
+  uint64_t* k_empty = k_full + KS;         // [KS]
+  uint64_t* v_full = k_empty + KS;         // [KS]
+  uint64_t* v_empty = v_full + KS;         // [KS]
+  uint64_t* s_full = v_empty + KS;         // [2]  QK_w(j) retired
+  uint64_t* p_full = s_full + 2;           // [2]  softmax_w(j) published P_w(j) (128 arrivals)
+  uint64_t* o_full = p_full + 2;           // [2]  PV_w(n-1) retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);   // [tile 2][half 2][row 128] partial max / sum
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int h = p.heads * D;
+  const int n_tiles = (p.S + ATT_BKV - 1) / ATT_BKV;
+  const int row_base = b * p.S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 256);
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // producer warpgroup: give its registers to the softmax warpgroups
+    setmaxnreg_dec<88>();
+    if (warp == 0) {
+      // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
+      if (elect_one_sync()) {
+        mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int a = 0; a < D / 64; ++a)
+            tma_load_2d(sQ + w * Cfg::TILE_BYTES + a * 16384, &tmQKV, q_full, head * D + a * 64,
+                        row_base + q0 + w * ATT_BQ);
+      }
+      __syncwarp();
+      int st = 0;
+      uint32_t par = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int kv_row = row_base + j * ATT_BKV;
+        mbar_wait(&k_empty[st], par ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int a = 0; a < D / 64; ++a)
+            tma_load_2d(sK + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &k_full[st], h + head * D + a * 64, kv_row);
+        }
+        __syncwarp();
+        mbar_wait(&v_empty[st], par ^ 1);
+        if (elect_one_sync()) {
+          mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
+#pragma unroll
+          for (int a = 0; a < D / 64; ++a)
+            tma_load_2d(sV + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &v_full[st], 2 * h + head * D + a * 64, kv_row);
+        }
+        __syncwarp();
+        if (++st == KS) {
+          st = 0;
+          par ^= 1;
+        }
+      }
+    } else if (warp == 1) {
+      // ------------------------------------------------------------------ MMA issuer (converged warp, elected issue)
+      constexpr uint32_t idesc_qk = make_idesc_f16(ATT_BQ, ATT_BKV, H16::is_bf16, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(ATT_BQ, D, H16::is_bf16, false, true);
+      const uint32_t desc_hi = smem_desc_hi_sw128(1024);
+      const uint32_t q_lo0 = smem_desc_lo(smem_u32(sQ), 0);
+      const uint32_t k_lo0 = smem_desc_lo(smem_u32(sK), 0);
+      const uint32_t v_lo0 = smem_desc_lo(smem_u32(sV), 16384);   // MN-major: LBO = stride between 64-wide d atoms
+      constexpr uint32_t TILE16 = Cfg::TILE_BYTES >> 4;
+      // S_w = Q_w K^T : K = d in 16-wide slices (slice k lives in 64-column atom k>>2 at +32 B * (k&3))
+      auto issue_qk = [&](int w, int st) {
+        const uint32_t q_lo = q_lo0 + w * TILE16;
+        const uint32_t k_lo = k_lo0 + st * TILE16;
+        const uint32_t d_tmem = tmem_base + Cfg::TMEM_S + w * 128;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = ((k >> 2) * 16384 + (k & 3) * 32) >> 4;
+          umma_ss(d_tmem, smem_desc_join(q_lo + off, desc_hi), smem_desc_join(k_lo + off, desc_hi), idesc_qk,
+                  k != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[w]);
+      };
+      // O_w += P_w V : A = P_w from TMEM (16 keys = 8 columns per slice), B = V slice of 16 key rows (2048 B apart)
+      auto issue_pv = [&](int w, int st, bool first) {
+        const uint32_t v_lo = v_lo0 + st * TILE16;
+        const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + w * 128;
+        const uint32_t d_tmem = tmem_base + Cfg::TMEM_O + w * 128;
+#pragma unroll
+        for (int k = 0; k < ATT_BKV / 16; ++k)
+          umma_ts(d_tmem, p_tmem + k * 8, smem_desc_join(v_lo + k * (2048 >> 4), desc_hi), idesc_pv,
+                  (!first || k != 0) ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        issue_qk(0, 0);
+        issue_qk(1, 0);
+        umma_commit(&k_empty[0]);
+      }
+      __syncwarp();
+      int st = 0;
+      uint32_t par = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st_n = (st + 1 == KS) ? 0 : st + 1;
+        const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
+        const bool more = j + 1 < n_tiles;
+        mbar_wait(&v_full[st], par);
+        if (p.debug < 4) mbar_wait(&p_full[0], j & 1);   // debug 4: tensor-side throughput without the softmax round trip
+        if (more) mbar_wait(&k_full[st_n], par_n);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          issue_pv(0, st, j == 0);
+          if (!more) umma_commit(&o_full[0]);
+          if (more) issue_qk(0, st_n);
+        }
+        __syncwarp();
+        if (p.debug < 4) mbar_wait(&p_full[1], j & 1);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          issue_pv(1, st, j == 0);
+          umma_commit(&v_empty[st]);
+          if (!more) umma_commit(&o_full[1]);
+          if (more) {
+            issue_qk(1, st_n);
+            umma_commit(&k_empty[st_n]);
+          }
+        }
+        __syncwarp();
+        st = st_n;
+        par = par_n;
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax warpgroups: g = 2*w + hh
+    setmaxnreg_inc<104>();
+    const int g = (warp - 4) >> 2;
+    const int w = g >> 1;       // Q tile
+    const int hh = g & 1;       // key half of every 128-key tile
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_s = t_lane + Cfg::TMEM_S + w * 128 + hh * 64;      // this thread's 64 scores
+    const uint32_t t_p = t_lane + Cfg::TMEM_S + w * 128 + hh * 32;      // its 32 packed P columns
+    constexpr int OC = D / 2;                                           // O columns owned by this half
+    const uint32_t t_o = t_lane + Cfg::TMEM_O + w * 128 + hh * OC;
+    float* my_x = xch + (w * 2 + hh) * 128 + r;
+    const float* peer_x = xch + (w * 2 + (hh ^ 1)) * 128 + r;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    const float sl2 = p.scale_log2;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[w], j & 1);
+      tc_fence_after();
+      const int kv_valid = p.S - j * ATT_BKV - hh * 64;   // valid keys in this half (tail tile only matters)
+      uint32_t sr[2][32];
+      tmem_ld_32x32(t_s, sr[0]);
+      tmem_ld_32x32(t_s + 32, sr[1]);
+      tmem_ld_wait();
+      if (kv_valid < 64) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+      }
+      const float mx_half = fmaxf(mx0, mx1);
+      *my_x = mx_half;
+      named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible, all S reads of this tile done
+      const float mx = fmaxf(mx_half, *peer_x) * sl2;
+      const float m_new = fmaxf(m_run, mx);
+      const bool need = (m_new - m_run) > 8.0f;   // identical in both halves (same inputs)
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = ex2_approx(m_run - m_new);
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+#pragma unroll
+          for (int c = 0; c < OC / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_o + c * 32, o);
+          }
+        }
+      }
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i]), sl2, -m_run));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i + 1]), sl2, -m_run));
+          ls0 += e0;
+          ls1 += e1;
+          pk[i] = H16::pack(e0, e1);
+        }
+        tmem_st_32x16(t_p + c * 16, pk);   // keys hh*64 + c*32 .. +31 -> P columns hh*32 + c*16 .. +15
+      }
+      l_run += ls0 + ls1;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[w]);
+    }
+
+    // epilogue: combine the two partial row sums, O_w / l -> global (each half writes its D/2 columns)
+    mbar_wait(&o_full[w], 0);
+    tc_fence_after();
+    *my_x = l_run;
+    named_bar_sync(1 + w, 256);
+    const float inv_l = 1.0f / (l_run + *peer_x);
+    const int s_idx = q0 + w * ATT_BQ + r;
+    const bool row_ok = s_idx < p.S;
+    T* dst = nullptr;
+    if (row_ok) {
+      if (s_idx < p.split)
+        dst = reinterpret_cast<T*>(p.out0) + (static_cast<long long>(b) * p.split + s_idx) * p.ld0 + head * D + hh * OC;
+      else
+        dst = reinterpret_cast<T*>(p.out1) +
+              (static_cast<long long>(b) * (p.S - p.split) + (s_idx - p.split)) * p.ld1 + head * D + hh * OC;
+    }
+#pragma unroll
+    for (int c = 0; c < OC / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_o + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          uint4 pk4;
+          pk4.x = H16::pack(__uint_as_float(o[gq * 8 + 0]) * inv_l, __uint_as_float(o[gq * 8 + 1]) * inv_l);
+          pk4.y = H16::pack(__uint_as_float(o[gq * 8 + 2]) * inv_l, __uint_as_float(o[gq * 8 + 3]) * inv_l);
+          pk4.z = H16::pack(__uint_as_float(o[gq * 8 + 4]) * inv_l, __uint_as_float(o[gq * 8 + 5]) * inv_l);
+          pk4.w = H16::pack(__uint_as_float(o[gq * 8 + 6]) * inv_l, __uint_as_float(o[gq * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + gq * 8) = pk4;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+template <typename T, int D>
+static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+  using Cfg = Att2Cfg<D>;
+  constexpr int SMEM = Cfg::SMEM_BYTES + 2 * 2 * 128 * 4;   // + partial max / sum exchange
+  auto kern = attention_fwd_v3_kernel<T, D>;
+  static bool configured = false;
+  if (!configured) {
+    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid(dk_ceil_div(p.S, 2 * ATT_BQ), p.heads, p.B);
+  kern<<<grid, ATT3_THREADS, SMEM, stream>>>(tm, p);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 template <typename T, int D, int POLY>
 static int launch_attention_v2p(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
   using Cfg = Att2Cfg<D>;
@@ -1061,6 +1383,18 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
     }
     if (d == 128) return launch_attention_v2a<__half, 128>(ctx, tm, p, stream);
     return launch_attention_v2a<__half, 64>(ctx, tm, p, stream);
+  }
+  static const bool use_v3 = [] {
+    const char* e = getenv("DK_ATTENTION_IMPL");
+    return e != nullptr && e[0] == '3';
+  }();
+  if (use_v3) {
+    if (dtype == DK_BF16) {
+      if (d == 128) return launch_attention_v3<__nv_bfloat16, 128>(ctx, tm, p, stream);
+      return launch_attention_v3<__nv_bfloat16, 64>(ctx, tm, p, stream);
+    }
+    if (d == 128) return launch_attention_v3<__half, 128>(ctx, tm, p, stream);
+    return launch_attention_v3<__half, 64>(ctx, tm, p, stream);
   }
   static const bool use_v1 = [] {
     const char* e = getenv("DK_ATTENTION_V1");
