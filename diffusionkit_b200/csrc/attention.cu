@@ -977,7 +977,10 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 // the per-thread row.  The two halves of a row exchange their partial row max through shared memory (one named
 // barrier per tile) so that both use the same running max; partial row sums are combined once at the end.
 // ================================================================================================
-constexpr int ATT3_THREADS = 640;
+// 18 warps: 0-15 softmax (g = warp >> 2, TMEM lane quarter = warp & 3), 16 TMA producer, 17 MMA issuer.
+// 576 threads -> 112 registers per thread at launch, enough for every role without setmaxnreg (a 640-thread layout
+// with setmaxnreg dead-locked: register redistribution is bounded by the CTA's launch allocation).
+constexpr int ATT3_THREADS = 576;
 
 template <typename T, int D>
 __global__ void __launch_bounds__(ATT3_THREADS, 1)
@@ -1011,7 +1014,7 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   const int n_tiles = (p.S + ATT_BKV - 1) / ATT_BKV;
   const int row_base = b * p.S;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     for (int i = 0; i < KS; ++i) {
@@ -1027,7 +1030,7 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 17) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -1036,10 +1039,8 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // producer warpgroup: give its registers to the softmax warpgroups
-    setmaxnreg_dec<88>();
-    if (warp == 0) {
+  if (warp >= 16) {
+    if (warp == 16) {
       // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(q_full, 2 * Cfg::TILE_BYTES);
@@ -1076,7 +1077,7 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
           par ^= 1;
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 17) {
       // ------------------------------------------------------------------ MMA issuer (converged warp, elected issue)
       constexpr uint32_t idesc_qk = make_idesc_f16(ATT_BQ, ATT_BKV, H16::is_bf16, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(ATT_BQ, D, H16::is_bf16, false, true);
@@ -1104,9 +1105,9 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + w * 128;
         const uint32_t d_tmem = tmem_base + Cfg::TMEM_O + w * 128;
 #pragma unroll
-        for (int k = 0; k < ATT_BKV / 16; ++k)
-          umma_ts(d_tmem, p_tmem + k * 8, smem_desc_join(v_lo + k * (2048 >> 4), desc_hi), idesc_pv,
-                  (!first || k != 0) ? 1u : 0u);
+        for (int k = 0; k < ATT_BKV / 16; ++k)   // keys 0-63 -> P columns [0,32), keys 64-127 -> P columns [64,96)
+          umma_ts(d_tmem, p_tmem + (k >> 2) * 64 + (k & 3) * 8, smem_desc_join(v_lo + k * (2048 >> 4), desc_hi),
+                  idesc_pv, (!first || k != 0) ? 1u : 0u);
       };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
@@ -1151,15 +1152,13 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     }
   } else {
     // -------------------------------------------------------------------- softmax warpgroups: g = 2*w + hh
-    setmaxnreg_inc<104>();
-    const int g = (warp - 4) >> 2;
+    const int g = warp >> 2;
     const int w = g >> 1;       // Q tile
     const int hh = g & 1;       // key half of every 128-key tile
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t t_s = t_lane + Cfg::TMEM_S + w * 128 + hh * 64;      // this thread's 64 scores
-    const uint32_t t_p = t_lane + Cfg::TMEM_S + w * 128 + hh * 32;      // its 32 packed P columns
     constexpr int OC = D / 2;                                           // O columns owned by this half
     const uint32_t t_o = t_lane + Cfg::TMEM_O + w * 128 + hh * OC;
     float* my_x = xch + (w * 2 + hh) * 128 + r;
@@ -1172,26 +1171,30 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
       const int kv_valid = p.S - j * ATT_BKV - hh * 64;   // valid keys in this half (tail tile only matters)
-      uint32_t sr[2][32];
-      tmem_ld_32x32(t_s, sr[0]);
-      tmem_ld_32x32(t_s + 32, sr[1]);
-      tmem_ld_wait();
-      if (kv_valid < 64) {
+      // pass 1: partial row max over this half's 64 scores
+      float mx_half;
+      {
+        uint32_t sr[2][32];
+        tmem_ld_32x32(t_s, sr[0]);
+        tmem_ld_32x32(t_s + 32, sr[1]);
+        tmem_ld_wait();
+        if (kv_valid < 64) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+        }
+        mx_half = fmaxf(mx0, mx1);
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
-      }
-      const float mx_half = fmaxf(mx0, mx1);
       *my_x = mx_half;
-      named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible, all S reads of this tile done
+      named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible
       const float mx = fmaxf(mx_half, *peer_x) * sl2;
       const float m_new = fmaxf(m_run, mx);
       const bool need = (m_new - m_run) > 8.0f;   // identical in both halves (same inputs)
@@ -1211,19 +1214,29 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
           }
         }
       }
+      // pass 2: P = exp2(s * sl2 - m_run) written over this half's OWN score columns (16 packed columns per 32 keys), so
+      // no thread ever overwrites scores another thread still has to read
       float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        uint32_t sc[32];
+        tmem_ld_32x32(t_s + c * 32, sc);
+        tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i]), sl2, -m_run));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sr[c][2 * i + 1]), sl2, -m_run));
+          float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
+          if (kv_valid < 64) {
+            if (c * 32 + 2 * i >= kv_valid) a0 = -INFINITY;
+            if (c * 32 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
+          }
+          const float e0 = ex2_approx(fmaf(a0, sl2, -m_run));
+          const float e1 = ex2_approx(fmaf(a1, sl2, -m_run));
           ls0 += e0;
           ls1 += e1;
           pk[i] = H16::pack(e0, e1);
         }
-        tmem_st_32x16(t_p + c * 16, pk);   // keys hh*64 + c*32 .. +31 -> P columns hh*32 + c*16 .. +15
+        tmem_st_32x16(t_s + c * 16, pk);
       }
       l_run += ls0 + ls1;
       tmem_st_wait();
@@ -1268,7 +1281,7 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
