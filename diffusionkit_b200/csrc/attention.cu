@@ -982,7 +982,8 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 // with setmaxnreg dead-locked: register redistribution is bounded by the CTA's launch allocation).
 constexpr int ATT3_THREADS = 576;
 
-template <typename T, int D>
+// POLY4: of every four exponentials, how many run on the FMA pipe (ex2_poly) instead of MUFU.EX2 (0, 1 or 2)
+template <typename T, int D, int POLY4>
 __global__ void __launch_bounds__(ATT3_THREADS, 1)
 attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
   using H16 = Half16<T>;
@@ -1230,8 +1231,9 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
             if (c * 32 + 2 * i >= kv_valid) a0 = -INFINITY;
             if (c * 32 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
           }
-          const float e0 = ex2_approx(fmaf(a0, sl2, -m_run));
-          const float e1 = ex2_approx(fmaf(a1, sl2, -m_run));
+          const float x0 = fmaf(a0, sl2, -m_run), x1 = fmaf(a1, sl2, -m_run);
+          const float e0 = ex2_approx(x0);
+          const float e1 = (POLY4 == 2 || (POLY4 == 1 && (i & 1))) ? ex2_poly(x1) : ex2_approx(x1);
           ls0 += e0;
           ls1 += e1;
           pk[i] = H16::pack(e0, e1);
@@ -1288,11 +1290,11 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 }
 
 
-template <typename T, int D>
-static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+template <typename T, int D, int POLY4>
+static int launch_attention_v3p(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
   using Cfg = Att2Cfg<D>;
   constexpr int SMEM = Cfg::SMEM_BYTES + 2 * 2 * 128 * 4;   // + partial max / sum exchange
-  auto kern = attention_fwd_v3_kernel<T, D>;
+  auto kern = attention_fwd_v3_kernel<T, D, POLY4>;
   static bool configured = false;
   if (!configured) {
     DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -1302,6 +1304,16 @@ static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttPara
   kern<<<grid, ATT3_THREADS, SMEM, stream>>>(tm, p);
   DK_LAUNCH_CHECK(ctx);
   return 0;
+}
+template <typename T, int D>
+static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+  static const int poly = [] {
+    const char* e = getenv("DK_ATT_POLY");
+    return e ? atoi(e) : 0;
+  }();
+  if (poly <= 0) return launch_attention_v3p<T, D, 0>(ctx, tm, p, stream);
+  if (poly == 1) return launch_attention_v3p<T, D, 1>(ctx, tm, p, stream);
+  return launch_attention_v3p<T, D, 2>(ctx, tm, p, stream);
 }
 
 template <typename T, int D, int POLY>
