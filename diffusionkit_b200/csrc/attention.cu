@@ -1409,9 +1409,11 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
     if (d == 128) return launch_attention_v2a<__half, 128>(ctx, tm, p, stream);
     return launch_attention_v2a<__half, 64>(ctx, tm, p, stream);
   }
+  // default: v3 (same-box A/B at the C4 shape: v3 1120, v2 1058, v2a 1064 TFLOP/s); DK_ATTENTION_IMPL=2 / 2a / 1 select
+  // the older kernels, DK_ATTENTION_V1=1 the first one
   static const bool use_v3 = [] {
     const char* e = getenv("DK_ATTENTION_IMPL");
-    return e != nullptr && e[0] == '3';
+    return e == nullptr || e[0] == '3';
   }();
   if (use_v3) {
     if (dtype == DK_BF16) {
@@ -1423,7 +1425,8 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
   }
   static const bool use_v1 = [] {
     const char* e = getenv("DK_ATTENTION_V1");
-    return e != nullptr && e[0] == '1';
+    const char* i = getenv("DK_ATTENTION_IMPL");
+    return (e != nullptr && e[0] == '1') || (i != nullptr && i[0] == '1');
   }();
   if (use_v1) {
     if (dtype == DK_BF16) {

@@ -226,22 +226,22 @@ def check_attention_d64():
 
 def check_attention_v1_kernel():
     """the single-Q-tile kernel with P staged through shared memory (DK_ATTENTION_V1=1) stays correct"""
-    os.environ["DK_ATTENTION_V1"] = "1"
+    os.environ["DK_ATTENTION_IMPL"] = "1"
     _setup()
     return {"d128": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att_v1_d128"),
             "d64": _attention_case(1, 1178, 2, 64, torch.float16, split=1024, name="att_v1_d64")}
 
 
-def check_attention_v3_kernel():
-    """two softmax warpgroups per Q tile (DK_ATTENTION_IMPL=3)"""
-    os.environ["DK_ATTENTION_IMPL"] = "3"
+def check_attention_v2_kernel():
+    """the one-softmax-warpgroup-per-Q-tile kernel (DK_ATTENTION_IMPL=2) stays correct; the default is v3"""
+    os.environ["DK_ATTENTION_IMPL"] = "2"
     _setup()
-    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att3_d128_S128"),
-           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att3_d128_S300"),
-           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att3_d128_S1280"),
-           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att3_d64_S1178"),
-           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att3_d64_S333"),
-           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att3_S1")}
+    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att2_d128_S128"),
+           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att2_d128_S300"),
+           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att2_d128_S1280"),
+           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att2_d64_S1178"),
+           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att2_d64_S333"),
+           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att2_S1")}
     out["rescale"] = check_attention_large_scores()["err"]
     return out
 
@@ -537,7 +537,7 @@ ALL_CHECKS = [
     check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
     check_gemm_pair_kernel, check_conv3x3,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
-    check_attention_v1_kernel, check_attention_v3_kernel,
+    check_attention_v1_kernel, check_attention_v2_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,
 ]
