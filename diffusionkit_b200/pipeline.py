@@ -153,8 +153,7 @@ class DiffusionPipeline:
             raise NotImplementedError(
                 "the B200 engine computes in 16-bit only: pass w16=True, a16=True (what the reference CLI forces, "
                 "scripts/generate_images.py:117-118)")
-        if local_ckpt is not None:
-            raise NotImplementedError("checkpoint loading (mlx/model_io.py) is SURVEY.md §8 row f1; pass `params`")
+        self._local_ckpt = local_ckpt
         self.dtype = self.float16_dtype
         self.activation_dtype = self.float16_dtype
         self.low_memory_mode = low_memory_mode
@@ -172,8 +171,39 @@ class DiffusionPipeline:
         self._params = self._vae_params = None      # the models hold packed copies; drop the caller's tensors
 
     # ------------------------------------------------------------------ model loading (:90-143)
+    def _load_local_ckpt(self):
+        """`local_ckpt`: path of an upstream .safetensors file (BFL FLUX / Stability SD3 layout), or a dict
+        {"mmdit": path, "vae": path}.  Key remapping: model_io.py (reference mlx/model_io.py:130-486)."""
+        from . import model_io
+
+        ck = self._local_ckpt
+        paths = ck if isinstance(ck, dict) else {"mmdit": ck}
+        out = {}
+        if paths.get("mmdit"):
+            sd = model_io.load_safetensors(paths["mmdit"])
+            if isinstance(self, FluxPipeline):
+                params = model_io.flux_checkpoint_to_params(sd, self.config.hidden_size, self.config.mlp_ratio)
+            else:
+                params = model_io.sd3_checkpoint_to_params(sd)
+                if "vae" not in paths and any("decoder." in k for k in sd):
+                    out["vae"] = model_io.vae_decoder_checkpoint_to_params(sd)     # single-file SD3 checkpoints
+            model_io.check_against_specs(params, mmdit_param_specs(self.config))
+            out["mmdit"] = params
+        if paths.get("vae"):
+            out["vae"] = model_io.vae_decoder_checkpoint_to_params(model_io.load_safetensors(paths["vae"]))
+        if "vae" in out:
+            model_io.check_against_specs(out["vae"], vae_decoder_param_specs(VAEDecoderConfig()))
+        return out
+
     def load_mmdit(self, only_modulation_dict=False):
         params = self._params
+        if params is None and self._local_ckpt is not None:
+            loaded = self._load_local_ckpt()
+            params = loaded.get("mmdit")
+            if self._vae_params is None:
+                self._vae_params = loaded.get("vae")
+            if params is not None:
+                params = {k: v.to(device=self.device, dtype=self.dtype) for k, v in params.items()}
         if params is None:
             params = init_params(mmdit_param_specs(self.config), seed=self._weight_seed, dtype=self.dtype,
                                  device=self.device)
@@ -255,7 +285,7 @@ class DiffusionPipeline:
 
         x_T = self.get_empty_latent(H, W)                                   # (1, H, W, 16) host
         if noise is None:
-            noise = torch.cat([self.get_noise(s, x_T) for s in seeds], dim=0)   # (B, H, W, 16) host fp32
+            noise = self._get_noise_batch(seeds, x_T)                              # (B, H, W, 16) host fp32
         elif tuple(noise.shape) != (B, H, W, 16):
             raise DkError(f"noise has shape {tuple(noise.shape)}, expected {(B, H, W, 16)}")
         sigmas = self.get_sigmas(self.sampler, num_steps)
@@ -327,7 +357,10 @@ class DiffusionPipeline:
         log["decoding"]["pre"] = mem()
         latents16 = ops.cast_to_16(latents, self.activation_dtype)          # latents.astype(activation_dtype) (:459)
         _, u8 = self._decode(latents16, want_u8=True)
-        images_u8 = u8.cpu().numpy()                                        # device -> host: the result
+        host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        host.copy_(u8, non_blocking=True)                                   # device -> host: the result
+        torch.cuda.current_stream().synchronize()
+        images_u8 = host.numpy()
         log["decoding"]["post"] = mem()
         log["decoding"]["time"] = round(time.time() - t0, 3)
         log["peak_memory"] = max(log["peak_memory"], log["decoding"]["post"]["peak_memory"])
@@ -341,10 +374,20 @@ class DiffusionPipeline:
 
     # ------------------------------------------------------------------ helpers (:553-584)
     def get_noise(self, seed, x_T):
-        np.random.seed(seed)
+        # np.random.seed(seed); np.random.randn(...) of the reference (:553-557).  RandomState(seed) is the same
+        # MT19937 stream as the seeded global generator, without the global state (thread-safe for batches).
         shape = tuple(x_T.shape)
-        noise = np.random.randn(shape[0], shape[3], shape[1], shape[2])
+        noise = np.random.RandomState(seed).randn(shape[0], shape[3], shape[1], shape[2])
         return torch.from_numpy(noise).permute(0, 2, 3, 1).to(torch.float32).contiguous()
+
+    def _get_noise_batch(self, seeds, x_T):
+        if len(seeds) == 1:
+            return self.get_noise(seeds[0], x_T)
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(len(seeds), 8)) as ex:   # numpy releases the GIL while drawing
+            parts = list(ex.map(lambda sd: self.get_noise(sd, x_T), seeds))
+        return torch.cat(parts, dim=0)
 
     def get_sigmas(self, sampler, num_steps: int):
         start = float(sampler.timestep(sampler.sigma_max))

@@ -192,6 +192,34 @@ def check_pipeline_errors():
     return {}
 
 
+def check_pipeline_local_ckpt():
+    """`local_ckpt=` (upstream BFL-layout .safetensors) produces the same latents as passing the parameter tree"""
+    import tempfile
+
+    from safetensors.torch import save_file
+
+    from tests.test_model_io_cpu import _flux_upstream, _vae_upstream
+
+    cfg = tiny_flux_config()
+    p32 = init_params(mmdit_param_specs(cfg), seed=7, dtype=torch.float32)
+    v32 = init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=8, dtype=torch.float32)
+    p16 = {k: v.to(torch.bfloat16) for k, v in p32.items()}
+    v16 = {k: v.to(torch.bfloat16) for k, v in v32.items()}
+    with tempfile.TemporaryDirectory() as d:
+        mm, va = os.path.join(d, "flux.safetensors"), os.path.join(d, "ae.safetensors")
+        save_file({k: v.contiguous() for k, v in _flux_upstream(p16, cfg).items()}, mm)
+        save_file({k: v.contiguous() for k, v in _vae_upstream(v16, prefix="decoder.").items()}, va)
+        a = dk.FluxPipeline(w16=True, a16=True, mmdit_config=cfg, local_ckpt={"mmdit": mm, "vae": va})
+    b = dk.FluxPipeline(w16=True, a16=True, mmdit_config=cfg, params={k: v.to(DEV) for k, v in p16.items()},
+                        vae_params={k: v.to(DEV) for k, v in v16.items()})
+    cond, pooled = a.synthetic_text_embeddings(text_len=16)
+    la, _ = a.denoise_latents(cond, pooled, num_steps=2, latent_size=(8, 8), seed=3)
+    lb, _ = b.denoise_latents(cond, pooled, num_steps=2, latent_size=(8, 8), seed=3)
+    assert torch.equal(la, lb)
+    assert torch.equal(a.decode_latents_to_image(la), b.decode_latents_to_image(lb))
+    return {}
+
+
 def check_full_size_flux_properties():
     """FLUX.1-schnell at its real width/depth (11.9 B synthetic parameters), 512x512, 4 steps: size-independent
     properties the oracle cannot check in seconds — determinism (no atomics on the path), batch independence
@@ -236,4 +264,4 @@ def check_full_size_vae_properties():
 
 ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
               check_vae_decode_tiny, check_vae_decode_batch_fp16, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
-              check_pipeline_errors, check_full_size_flux_properties, check_full_size_vae_properties]
+              check_pipeline_errors, check_pipeline_local_ckpt, check_full_size_flux_properties, check_full_size_vae_properties]

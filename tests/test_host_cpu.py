@@ -135,6 +135,19 @@ def test_product_schedules_match_kats():
     assert float(p.get_empty_latent(2, 2)[0, 0, 0, 0]) == np.float32(0.0609)
 
 
+def test_get_noise_equals_global_numpy_rng():
+    """RandomState(seed) reproduces the reference's np.random.seed(seed); np.random.randn(...) draw exactly, and the
+    threaded batch path equals per-seed draws"""
+    p = _bare(DiffusionPipeline, ModelSamplingDiscreteFlow(3.0))
+    x_T = p.get_empty_latent(6, 10)
+    for seed in (0, 7, 123456):
+        np.random.seed(seed)
+        want = torch.from_numpy(np.random.randn(1, 16, 6, 10)).permute(0, 2, 3, 1).to(torch.float32)
+        assert torch.equal(p.get_noise(seed, x_T), want)
+    batch = p._get_noise_batch([3, 4, 5], x_T)
+    assert torch.equal(batch, torch.cat([p.get_noise(s, x_T) for s in (3, 4, 5)]))
+
+
 def test_latent_formats():
     assert dk.SD3LatentFormat().process_out(0.0) == 0.0609 and abs(dk.FluxLatentFormat().process_out(0.3611) - 1.1159) < 1e-12
     lf = dk.FluxLatentFormat()
