@@ -8,11 +8,11 @@ DiffusionPipeline / FluxPipeline API (reference: argmaxinc/DiffusionKit, python/
                                      conditioning=cond, pooled_conditioning=pooled)
 """
 from ._lib import DkError  # noqa: F401
-from .config import FLUX_DEV, FLUX_SCHNELL, SD3_2b, SD3_8b, MMDiTConfig, VAEDecoderConfig  # noqa: F401
+from .config import FLUX_DEV, FLUX_SCHNELL, SD3_2b, SD3_8b, MMDiTConfig, VAEDecoderConfig, VAEEncoderConfig  # noqa: F401
 from .mmdit import MMDiT  # noqa: F401
 from .pipeline import (CFGDenoiser, DiffusionPipeline, FluxLatentFormat, FluxPipeline, LatentFormat,  # noqa: F401
                        SD3LatentFormat, sample_euler)
 from .sampler import FluxSampler, ModelSamplingDiscreteFlow  # noqa: F401
-from .vae import VAEDecoder  # noqa: F401
+from .vae import VAEDecoder, VAEEncoder  # noqa: F401
 
 __version__ = "0.1.0"

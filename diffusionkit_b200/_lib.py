@@ -62,12 +62,16 @@ SIGNATURES = {
     "dk_sampler_prepare": (i32, [vp, i32, vp, vp, i64, i32, vp]),
     "dk_sampler_step": (i32, [vp, i32, vp, vp, vp, i64, f32, f32, f32, vp]),
     "dk_axpb_f32": (i32, [vp, vp, vp, i64, f32, f32, vp]),
+    "dk_image_pre": (i32, [vp, i32, vp, vp, i64, i32, i32, vp]),
+    "dk_axpby_f32": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),
+    "dk_vae_sample_latent": (i32, [vp, i32, vp, vp, vp, i64, i32, f32, f32, vp]),
     "dk_cast_f32_to_16": (i32, [vp, i32, vp, vp, i64, vp]),
     "dk_cast_16_to_f32": (i32, [vp, i32, vp, vp, i64, vp]),
     "dk_groupnorm_ws_floats": (i32, [i32, i32]),
     "dk_groupnorm_stats": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, f32, vp]),
     "dk_groupnorm_apply": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "dk_conv3x3": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "dk_conv3x3_s2": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "dk_upsample_nearest2x": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
     "dk_softmax_rows": (i32, [vp, i32, vp, i64, i32, i64, f32, vp]),
     "dk_image_post": (i32, [vp, i32, vp, i32, vp, vp, i64, vp]),

@@ -85,6 +85,17 @@ class VAEDecoderConfig:
     resnet_groups: int = 32
 
 
+@dataclass
+class VAEEncoderConfig:
+    """reference mlx/config.py:135-141"""
+
+    in_channels: int = 3
+    out_channels: int = 32
+    block_out_channels: Tuple[int, ...] = (128, 256, 512, 512)
+    layers_per_block: int = 2
+    resnet_groups: int = 32
+
+
 # model_version -> config, as the reference's loader resolves it (mlx/model_io.py:105-112)
 MODEL_CONFIGS = {
     "argmaxinc/mlx-stable-diffusion-3-medium": SD3_2b,

@@ -50,7 +50,7 @@ extern "C" void dk_ctx_destroy(dk_ctx* ctx) {
 extern "C" long long dk_ctx_launch_count(dk_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int dk_make_tmap_16b(dk_ctx* ctx, CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box) {
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bdim[5];
@@ -58,7 +58,7 @@ int dk_make_tmap_16b(dk_ctx* ctx, CUtensorMap* map, const void* base, int rank, 
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   // the data type only matters for OOB-fill / element size; bf16 and fp16 are both 2-byte tiles

@@ -326,6 +326,52 @@ __global__ void axpb_kernel(const float* __restrict__ x, float* __restrict__ y, 
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = x[i] * a + b;
 }
+// read_image (reference mlx/__init__.py:536-551): uint8 [pixels, src_c >= 3] -> 16-bit [pixels, cpad], channels 0..2 =
+// u8 / 255 * 2 - 1 (fp32 arithmetic, then rounded to T), channels 3.. = 0 (the tensor-core conv wants Cin % 64 == 0)
+template <typename T>
+__global__ void image_pre_kernel(const uint8_t* __restrict__ img, T* __restrict__ out, long long pixels, int src_c,
+                                 int cpad) {
+  const int vpp = cpad / 8;
+  const long long nvec = pixels * vpp;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / vpp;
+    const int v = static_cast<int>(i - p * vpp);
+    uint4 w = make_uint4(0u, 0u, 0u, 0u);
+    if (v == 0) {
+      const uint8_t* px = img + p * src_c;
+      // three separately rounded fp32 ops like the reference's (x / 255) * 2 - 1 (no FMA contraction)
+      const float r = __fsub_rn(__fmul_rn(__fdiv_rn(static_cast<float>(px[0]), 255.f), 2.f), 1.f);
+      const float g = __fsub_rn(__fmul_rn(__fdiv_rn(static_cast<float>(px[1]), 255.f), 2.f), 1.f);
+      const float b = __fsub_rn(__fmul_rn(__fdiv_rn(static_cast<float>(px[2]), 255.f), 2.f), 1.f);
+      w.x = Half16<T>::pack(r, g);
+      w.y = Half16<T>::pack(b, 0.f);
+    }
+    *reinterpret_cast<uint4*>(out + p * cpad + v * 8) = w;
+  }
+}
+__global__ void axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ o,
+                             long long n, float a, float b) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    o[i] = a * x[i] + b * y[i];
+}
+// VAE encoder posterior sample (reference mlx/__init__.py:586-594) + latent_format.process_in (:729-730):
+//   hidden [pixels, 2C] = (mean | logvar); z = mean + exp(0.5 * clip(logvar, -30, 20)) * noise; out = (z - shift) * scale
+template <typename T>
+__global__ void vae_sample_latent_kernel(const T* __restrict__ hidden, const float* __restrict__ noise,
+                                         float* __restrict__ out, long long pixels, int C, float shift, float scale) {
+  const long long n = pixels * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / C;
+    const int c = static_cast<int>(i - p * C);
+    const float mean = Half16<T>::to_f(hidden[p * 2 * C + c]);
+    const float logvar = fminf(fmaxf(Half16<T>::to_f(hidden[p * 2 * C + C + c]), -30.f), 20.f);
+    const float z = mean + __expf(0.5f * logvar) * noise[i];
+    out[i] = (z - shift) * scale;
+  }
+}
 template <typename T>
 __global__ void cast_f32_to_16_kernel(const float* __restrict__ x, T* __restrict__ y, long long n) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -788,6 +834,39 @@ extern "C" int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, f
   DK_REQUIRE(ctx != nullptr, "dk_axpb_f32: null ctx");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   axpb_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(x, y, n, a, b);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_image_pre(dk_ctx* ctx, int dtype, const uint8_t* img, void* out, long long pixels, int src_channels,
+                            int cpad, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_image_pre: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(src_channels >= 3, "dk_image_pre: image needs at least 3 channels (got %d)", src_channels);
+  DK_REQUIRE(cpad >= 8 && cpad % 8 == 0, "dk_image_pre: cpad (%d) must be a positive multiple of 8", cpad);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (image_pre_kernel<T><<<grid_for(pixels * (cpad / 8), 256, ctx->sm_count), 256, 0, stream>>>(
+                         img, static_cast<T*>(out), pixels, src_channels, cpad)));
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_axpby_f32(dk_ctx* ctx, const float* x, const float* y, float* out, long long n, float a, float b,
+                            void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_axpby_f32: null ctx");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  axpby_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(x, y, out, n, a, b);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_vae_sample_latent(dk_ctx* ctx, int dtype, const void* hidden, const float* noise, float* out,
+                                    long long pixels, int C, float shift, float scale, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_vae_sample_latent: null ctx");
+  DK_DTYPE_OK(dtype);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (vae_sample_latent_kernel<T><<<grid_for(pixels * C, 256, ctx->sm_count), 256, 0, stream>>>(
+                         static_cast<const T*>(hidden), noise, out, pixels, C, shift, scale)));
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -128,7 +128,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int tap = kb / g.cblocks;
             const int c0 = (kb - tap * g.cblocks) * BK;
             const int dy = tap / 3, dx = tap - dy * 3;
-            tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, x0 + dx - 1, y0 + dy - 1, img);
+            tma_load_4d(a_dst, &tmA, &full_bar[stage], c0, x0 * g.stride + dx - g.pad, y0 * g.stride + dy - g.pad, img);
           }
           if (!B_MN) {
             tma_load_2d(b_dst, &tmB, &full_bar[stage], kb * BK, n_blk * BN);
@@ -389,23 +389,26 @@ extern "C" int dk_gemm(dk_ctx* ctx, const dk_gemm_args* a, void* stream_) {
   }
 }
 
-extern "C" int dk_conv3x3(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, const void* res,
-                          void* out, int B, int H, int W, int Cin, int Cout, void* stream_) {
+static int conv3x3_impl(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, const void* res,
+                        void* out, int B, int Hin, int Win, int Cin, int Cout, int stride, cudaStream_t stream) {
   DK_REQUIRE(ctx != nullptr, "dk_conv3x3: null ctx");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DK_REQUIRE(dtype == DK_BF16 || dtype == DK_FP16, "dk_conv3x3: bad dtype %d", dtype);
-  DK_REQUIRE(B > 0 && H > 0 && W > 0, "dk_conv3x3: empty input");
+  DK_REQUIRE(B > 0 && Hin > 0 && Win > 0, "dk_conv3x3: empty input");
   DK_REQUIRE(Cin % 64 == 0, "dk_conv3x3: Cin (%d) must be a multiple of 64 (pad the channels)", Cin);
   DK_REQUIRE(Cout % 8 == 0, "dk_conv3x3: Cout (%d) must be a multiple of 8 (pad the filters)", Cout);
   DK_REQUIRE(aligned16(x) && aligned16(w) && aligned16(out), "dk_conv3x3: x/w/out must be 16-byte aligned");
   DK_REQUIRE(bias == nullptr || aligned16(bias), "dk_conv3x3: bias alignment");
   DK_REQUIRE(res == nullptr || aligned16(res), "dk_conv3x3: residual alignment");
+  DK_REQUIRE(stride == 1 || (Hin % 2 == 0 && Win % 2 == 0), "dk_conv3x3_s2: input size must be even (got %dx%d)", Hin, Win);
 
+  const int H = Hin / stride, W = Win / stride;   // output size
   ConvGeom g;
   g.B = B;
   g.H = H;
   g.W = W;
   g.Cin = Cin;
+  g.stride = stride;
+  g.pad = stride == 1 ? 1 : 0;
   if (W < 128 && 128 % W == 0) {
     g.TW = W;
     g.TH = 128 / W;
@@ -437,12 +440,15 @@ extern "C" int dk_conv3x3(dk_ctx* ctx, int dtype, const void* x, const void* w, 
 
   CUtensorMap tmA, tmB;
   {
-    const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+    const uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Win), static_cast<uint64_t>(Hin),
                               static_cast<uint64_t>(B)};
-    const uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(W) * Cin * 2,
-                                 static_cast<uint64_t>(H) * W * Cin * 2};
-    const uint32_t box[4] = {BK, static_cast<uint32_t>(g.TW), static_cast<uint32_t>(g.TH), 1};
-    if (int rc = dk_make_tmap_16b(ctx, &tmA, x, 4, dims, strides, box)) return rc;
+    const uint64_t strides[3] = {static_cast<uint64_t>(Cin) * 2, static_cast<uint64_t>(Win) * Cin * 2,
+                                 static_cast<uint64_t>(Hin) * Win * Cin * 2};
+    // strided traversal: N elements with stride s need a box entry of N * s
+    const uint32_t box[4] = {BK, static_cast<uint32_t>(g.TW * stride), static_cast<uint32_t>(g.TH * stride), 1};
+    const uint32_t estr[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+    DK_REQUIRE(box[1] <= 256 && box[2] <= 256, "dk_conv3x3: TMA box too large");
+    if (int rc = dk_make_tmap_16b(ctx, &tmA, x, 4, dims, strides, box, estr)) return rc;
   }
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(9 * Cin), static_cast<uint64_t>(Cout)};
@@ -452,4 +458,14 @@ extern "C" int dk_conv3x3(dk_ctx* ctx, int dtype, const void* x, const void* w, 
   }
   if (dtype == DK_BF16) return launch_gemm_bn<__nv_bfloat16, false, 1>(ctx, bn, tmA, tmB, s, e, g, stream);
   return launch_gemm_bn<__half, false, 1>(ctx, bn, tmA, tmB, s, e, g, stream);
+}
+
+extern "C" int dk_conv3x3(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, const void* res,
+                          void* out, int B, int H, int W, int Cin, int Cout, void* stream_) {
+  return conv3x3_impl(ctx, dtype, x, w, bias, res, out, B, H, W, Cin, Cout, 1, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int dk_conv3x3_s2(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, void* out, int B,
+                             int H, int W, int Cin, int Cout, void* stream_) {
+  return conv3x3_impl(ctx, dtype, x, w, bias, nullptr, out, B, H, W, Cin, Cout, 2, static_cast<cudaStream_t>(stream_));
 }

@@ -34,7 +34,9 @@ struct GemmEpi {
 };
 
 struct ConvGeom {
-  int B, H, W, Cin;
+  int B, H, W, Cin;      // H, W: OUTPUT size
+  int stride, pad;       // stride 1 / pad 1 (symmetric), or stride 2 / pad 0 with an implicit zero row+column at the
+                         // bottom/right (mlx: pad [(0,1),(0,1)] then stride-2 conv, vae.py:142-144)
   int TH, TW;            // output-pixel tile: TH x TW = 128
   int tiles_x, tiles_y;  // per image
   int cblocks;           // Cin / 64

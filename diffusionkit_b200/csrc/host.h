@@ -54,7 +54,9 @@ void dk_set_error(const char* fmt, ...);
 
 // Tiled tensor map over a 16-bit tensor, 128B swizzle, zero OOB fill.
 //   rank 2..4; dims[0] is the contiguous dimension; strides_bytes has rank-1 entries (dims 1..).
+//   elem_strides (optional, rank entries): traversal stride per dimension; to load N elements with stride s the box
+//   entry must be N * s (cuTensorMapEncodeTiled semantics).
 int dk_make_tmap_16b(dk_ctx* ctx, CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
-                     const uint64_t* strides_bytes, const uint32_t* box);
+                     const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 static inline int dk_ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -4,7 +4,7 @@ this engine consumes (the reference's module-tree names).
 Restates the rules of the reference loaders (python/src/diffusionkit/mlx/model_io.py):
   flux_state_dict_adjustments        :130-311
   mmdit_state_dict_adjustments       :314-408
-  vae_decoder_state_dict_adjustments :411-486
+  vae_decoder_state_dict_adjustments :411-486, vae_encoder_state_dict_adjustments :489-571
 as table-driven converters over torch tensors.  SURVEY.md §8 "next" row f1.  Downloading (huggingface_hub) is out of
 scope — callers pass a local .safetensors path (the reference's `local_ckpt`).
 """
@@ -171,11 +171,11 @@ def sd3_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "model.diffusi
     return out
 
 
-# ------------------------------------------------------------------------------------------------ VAE decoder (LDM layout)
-def vae_decoder_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "decoder.") -> Dict[str, Tensor]:
-    """LDM autoencoder `decoder.*` -> VAEDecoder parameter tree (reference model_io.py:411-486).
-    `prefix` may sit behind another prefix (e.g. `first_stage_model.decoder.`): everything up to and including the first
-    occurrence of `prefix` is stripped."""
+# ------------------------------------------------------------------------------------------------ VAE (LDM layout)
+def _vae_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str, side: str) -> Dict[str, Tensor]:
+    """LDM autoencoder `<prefix>*` -> VAEDecoder / VAEEncoder parameter tree.  side = "up" (decoder: up.N.block.M,
+    up.N.upsample.conv) or "down" (encoder: down.N.block.M, down.N.downsample.conv)."""
+    blocks, sample = f"{side}_blocks", f"{side}sample"
     out: Dict[str, Tensor] = {}
     for key, v in sd.items():
         pos = key.find(prefix)
@@ -183,20 +183,20 @@ def vae_decoder_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "decod
             continue
         k = key[pos + len(prefix):]
         leaf = k.rsplit(".", 1)[1]
-        m = re.fullmatch(r"up\.(\d+)\.block\.(\d+)\.(norm1|conv1|norm2|conv2|nin_shortcut)\.(weight|bias)", k)
+        m = re.fullmatch(side + r"\.(\d+)\.block\.(\d+)\.(norm1|conv1|norm2|conv2|nin_shortcut)\.(weight|bias)", k)
         if m:
             j, l, mod, _ = m.groups()
             if mod == "nin_shortcut":
-                name, val = f"up_blocks.{j}.resnets.{l}.conv_shortcut.{leaf}", (v[:, :, 0, 0].contiguous() if leaf == "weight" else v)
+                name, val = f"{blocks}.{j}.resnets.{l}.conv_shortcut.{leaf}", (v[:, :, 0, 0].contiguous() if leaf == "weight" else v)
             elif mod.startswith("conv"):
-                name, val = f"up_blocks.{j}.resnets.{l}.{mod}.{leaf}", (_conv_oihw_to_ohwi(v) if leaf == "weight" else v)
+                name, val = f"{blocks}.{j}.resnets.{l}.{mod}.{leaf}", (_conv_oihw_to_ohwi(v) if leaf == "weight" else v)
             else:
-                name, val = f"up_blocks.{j}.resnets.{l}.{mod}.{leaf}", v
+                name, val = f"{blocks}.{j}.resnets.{l}.{mod}.{leaf}", v
             out[name] = val
             continue
-        m = re.fullmatch(r"up\.(\d+)\.upsample\.conv\.(weight|bias)", k)
+        m = re.fullmatch(side + r"\.(\d+)\." + sample + r"\.conv\.(weight|bias)", k)
         if m:
-            out[f"up_blocks.{m.group(1)}.upsample.{leaf}"] = _conv_oihw_to_ohwi(v) if leaf == "weight" else v
+            out[f"{blocks}.{m.group(1)}.{sample}.{leaf}"] = _conv_oihw_to_ohwi(v) if leaf == "weight" else v
             continue
         m = re.fullmatch(r"mid\.block_(1|2)\.(norm1|conv1|norm2|conv2)\.(weight|bias)", k)
         if m:
@@ -216,8 +216,20 @@ def vae_decoder_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "decod
         elif k.startswith("norm_out."):
             out["conv_norm_out." + leaf] = v
         else:
-            raise KeyError(f"unrecognised VAE decoder key {key}")
+            raise KeyError(f"unrecognised VAE {'decoder' if side == 'up' else 'encoder'} key {key}")
     return out
+
+
+def vae_decoder_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "decoder.") -> Dict[str, Tensor]:
+    """LDM autoencoder `decoder.*` -> VAEDecoder parameter tree (reference model_io.py:411-486).
+    `prefix` may sit behind another prefix (e.g. `first_stage_model.decoder.`): everything up to and including the first
+    occurrence of `prefix` is stripped."""
+    return _vae_checkpoint_to_params(sd, prefix, "up")
+
+
+def vae_encoder_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "encoder.") -> Dict[str, Tensor]:
+    """LDM autoencoder `encoder.*` -> VAEEncoder parameter tree (reference model_io.py:489-571)."""
+    return _vae_checkpoint_to_params(sd, prefix, "down")
 
 
 def check_against_specs(params: Dict[str, Tensor], specs: Iterable[Tuple[str, Tuple[int, ...], str]],

@@ -234,6 +234,40 @@ def axpb(x, a: float, b: float, out=None):
     return out
 
 
+def image_pre(img_u8, dtype, cpad: int = 64):
+    """uint8 NHWC [B,H,W,>=3] -> 16-bit NHWC [B,H,W,cpad] in [-1, 1] (channels 3.. zero)"""
+    assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and img_u8.dim() == 4 and img_u8.is_cuda
+    B, H, W, Cs = img_u8.shape
+    out = torch.empty((B, H, W, cpad), dtype=dtype, device=img_u8.device)
+    c = ctx(img_u8.device.index)
+    c.call("dk_image_pre", dtype_code(dtype), ptr(img_u8), ptr(out), B * H * W, Cs, cpad)
+    return out
+
+
+def axpby(x, y, a: float, b: float, out=None):
+    assert x.dtype == torch.float32 and y.dtype == torch.float32 and x.is_contiguous() and y.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    c = ctx(x.device.index)
+    c.call("dk_axpby_f32", ptr(x), ptr(y), ptr(out), x.numel(), a, b)
+    return out
+
+
+def vae_sample_latent(hidden, noise, shift: float, scale: float, out=None):
+    """hidden NHWC [B,H,W,2C] 16-bit (mean | logvar), noise fp32 [B,H,W,C] -> process_in(mean + std * noise) fp32"""
+    _chk16(hidden, "vae_sample_latent.hidden")
+    B, H, W, C2 = hidden.shape
+    assert hidden.is_contiguous() and noise.dtype == torch.float32 and noise.is_contiguous()
+    assert tuple(noise.shape) == (B, H, W, C2 // 2)
+    if out is None:
+        out = torch.empty((B, H, W, C2 // 2), dtype=torch.float32, device=hidden.device)
+    assert out.dtype == torch.float32 and out.is_contiguous()
+    c = ctx(hidden.device.index)
+    c.call("dk_vae_sample_latent", dtype_code(hidden.dtype), ptr(hidden), ptr(noise), ptr(out), B * H * W, C2 // 2,
+           shift, scale)
+    return out
+
+
 def cast_to_16(x, dtype, out=None):
     assert x.dtype == torch.float32 and x.is_contiguous()
     if out is None:
@@ -287,6 +321,19 @@ def conv3x3(x, w, bias=None, res=None, out=None):
         out = torch.empty((B, H, W, Cout), dtype=x.dtype, device=x.device)
     c = ctx(x.device.index)
     c.call("dk_conv3x3", dtype_code(x.dtype), ptr(x), ptr(w), ptr(bias), ptr(res), ptr(out), B, H, W, Cin, Cout)
+    return out
+
+
+def conv3x3_s2(x, w, bias=None, out=None):
+    """stride-2 3x3 conv with bottom/right zero padding: x NHWC [B,H,W,Cin] -> [B,H/2,W/2,Cout]"""
+    _chk16(x, "conv3x3_s2.x")
+    B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape == (Cout, 3, 3, Cin) and x.is_contiguous() and w.is_contiguous()
+    if out is None:
+        out = torch.empty((B, H // 2, W // 2, Cout), dtype=x.dtype, device=x.device)
+    c = ctx(x.device.index)
+    c.call("dk_conv3x3_s2", dtype_code(x.dtype), ptr(x), ptr(w), ptr(bias), ptr(out), B, H, W, Cin, Cout)
     return out
 
 

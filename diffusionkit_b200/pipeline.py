@@ -22,11 +22,11 @@ import torch
 
 from . import ops
 from ._lib import DkError
-from .config import MODEL_CONFIGS, T5_MAX_LENGTH, MMDiTConfig, VAEDecoderConfig
+from .config import MODEL_CONFIGS, T5_MAX_LENGTH, MMDiTConfig, VAEDecoderConfig, VAEEncoderConfig
 from .mmdit import MMDiT
 from .sampler import FluxSampler, ModelSamplingDiscreteFlow
-from .vae import VAEDecoder
-from .weights import init_params, mmdit_param_specs, vae_decoder_param_specs
+from .vae import VAEDecoder, VAEEncoder
+from .weights import init_params, mmdit_param_specs, vae_decoder_param_specs, vae_encoder_param_specs
 
 MMDIT_CKPT = {  # reference mlx/__init__.py:37-44 (quantised / SD3.5 variants: SURVEY.md §8 row f4)
     "argmaxinc/mlx-stable-diffusion-3-medium": "argmaxinc/mlx-stable-diffusion-3-medium",
@@ -137,8 +137,11 @@ class DiffusionPipeline:
         mmdit_config: Optional[MMDiTConfig] = None,
         weight_seed: int = 0,
         load_decoder: bool = True,
+        vae_encoder_params: Optional[Dict[str, torch.Tensor]] = None,
+        load_encoder: bool = False,
     ):
         self.float16_dtype = torch.float16                                  # :76 (quirk Q10)
+        self._vae_encoder_params, self._load_encoder = vae_encoder_params, load_encoder
         self._setup(w16, a16, shift, model_version, low_memory_mode, local_ckpt, device, params, vae_params,
                     mmdit_config, weight_seed, load_decoder)
         self.use_t5 = use_t5
@@ -169,6 +172,8 @@ class DiffusionPipeline:
         self._load_decoder = load_decoder
         self.check_and_load_models()
         self._params = self._vae_params = None      # the models hold packed copies; drop the caller's tensors
+        if hasattr(self, "encoder"):
+            self._vae_encoder_params = None
 
     # ------------------------------------------------------------------ model loading (:90-143)
     def _load_local_ckpt(self):
@@ -187,12 +192,19 @@ class DiffusionPipeline:
                 params = model_io.sd3_checkpoint_to_params(sd)
                 if "vae" not in paths and any("decoder." in k for k in sd):
                     out["vae"] = model_io.vae_decoder_checkpoint_to_params(sd)     # single-file SD3 checkpoints
+                if "vae" not in paths and any("encoder.down." in k for k in sd):
+                    out["vae_encoder"] = model_io.vae_encoder_checkpoint_to_params(sd)
             model_io.check_against_specs(params, mmdit_param_specs(self.config))
             out["mmdit"] = params
         if paths.get("vae"):
-            out["vae"] = model_io.vae_decoder_checkpoint_to_params(model_io.load_safetensors(paths["vae"]))
+            vsd = model_io.load_safetensors(paths["vae"])
+            out["vae"] = model_io.vae_decoder_checkpoint_to_params(vsd)
+            if any("encoder.down." in k for k in vsd):                             # ae.safetensors holds both halves
+                out["vae_encoder"] = model_io.vae_encoder_checkpoint_to_params(vsd)
         if "vae" in out:
             model_io.check_against_specs(out["vae"], vae_decoder_param_specs(VAEDecoderConfig()))
+        if "vae_encoder" in out:
+            model_io.check_against_specs(out["vae_encoder"], vae_encoder_param_specs(VAEEncoderConfig()))
         return out
 
     def load_mmdit(self, only_modulation_dict=False):
@@ -202,6 +214,8 @@ class DiffusionPipeline:
             params = loaded.get("mmdit")
             if self._vae_params is None:
                 self._vae_params = loaded.get("vae")
+            if self._vae_encoder_params is None:
+                self._vae_encoder_params = loaded.get("vae_encoder")
             if params is not None:
                 params = {k: v.to(device=self.device, dtype=self.dtype) for k, v in params.items()}
         if params is None:
@@ -218,6 +232,20 @@ class DiffusionPipeline:
                 vp = init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=self._weight_seed + 1,
                                  dtype=self.dtype, device=self.device)
             self.decoder = VAEDecoder(vp, VAEDecoderConfig(), device=self.device)
+        if not hasattr(self, "encoder") and self._load_encoder:
+            self.load_encoder()
+
+    def load_encoder(self):
+        """reference check_and_load_models (:115-116) loads the encoder eagerly; here it is built on the first img2img
+        call (or at construction with load_encoder=True) so text-to-image runs do not carry its 34 M parameters."""
+        ep = self._vae_encoder_params
+        if ep is None:
+            ep = init_params(vae_encoder_param_specs(VAEEncoderConfig()), seed=self._weight_seed + 2,
+                             dtype=self.dtype, device=self.device)
+        else:
+            ep = {k: v.to(device=self.device, dtype=self.dtype) for k, v in ep.items()}
+        self.encoder = VAEEncoder(ep, VAEEncoderConfig(), device=self.device)
+        self._vae_encoder_params = None
 
     # ------------------------------------------------------------------ text (row f2: not on the hot path)
     def encode_text(self, text: str, cfg_weight: float = 7.5, negative_text: str = ""):
@@ -260,10 +288,13 @@ class DiffusionPipeline:
         noise: Optional[torch.Tensor] = None,
     ):
         """-> (latent NHWC (B, H, W, 16) fp32 on the device, iter_time list).  `noise` (optional, device fp32
-        (B, H, W, 16)) replaces the host-side numpy draw of get_noise for callers whose inputs already live in HBM."""
-        if image_path is not None:
-            raise NotImplementedError("img2img needs the VAE encoder (SURVEY.md §8 row f3)")
-        denoise = 1.0
+        (B, H, W, 16)) replaces the host-side numpy draw of get_noise for callers whose inputs already live in HBM.
+        `image_path` (img2img): a file path, a PIL image or a uint8 HWC array; the latent size then follows the image
+        (the reference ignores latent_size in that case too, :273)."""
+        if image_path is None:
+            denoise = 1.0                                                   # :270-271
+        elif not (0.0 <= denoise <= 1.0):
+            raise ValueError(f"denoise must be in [0, 1], got {denoise}")
         seeds: List[int]
         if seed is None:
             seeds = [int(time.time())]
@@ -283,6 +314,10 @@ class DiffusionPipeline:
                 f"conditioning has batch {conditioning.shape[0]}, expected {reps * B} "
                 f"({'[positive | negative] x ' if reps == 2 else ''}{B} image(s)) for cfg_weight={cfg_weight}")
 
+        hidden = None
+        if image_path is not None:
+            hidden = self._encode_image_hidden(image_path)                  # (1, H, W, 32) = (mean | logvar)
+            H, W = hidden.shape[1], hidden.shape[2]
         x_T = self.get_empty_latent(H, W)                                   # (1, H, W, 16) host
         if noise is None:
             noise = self._get_noise_batch(seeds, x_T)                              # (B, H, W, 16) host fp32
@@ -290,10 +325,20 @@ class DiffusionPipeline:
             raise DkError(f"noise has shape {tuple(noise.shape)}, expected {(B, H, W, 16)}")
         sigmas = self.get_sigmas(self.sampler, num_steps)
         sigmas = sigmas[int(num_steps * (1 - denoise)):]
-        x = noise.to(self.device, dtype=torch.float32, non_blocking=True).clone()
-        # noise_scaling: sigma0 * noise + (1 - sigma0) * x_T (sampler.py:41-42); x_T is the constant 0.0609
         s0 = float(sigmas[0])
-        x = ops.axpb(x.contiguous(), s0, (1.0 - s0) * 0.0609)
+        if hidden is None:
+            x = noise.to(self.device, dtype=torch.float32, non_blocking=True).clone()
+            # noise_scaling: sigma0 * noise + (1 - sigma0) * x_T (sampler.py:41-42); x_T is the constant 0.0609
+            x = ops.axpb(x.contiguous(), s0, (1.0 - s0) * 0.0609)
+        else:
+            # x_T = process_in(mean + std * noise), with the SAME seeded draw the diffusion noise uses (:273-275,
+            # :586-594: both get_noise(seed, .) calls see the same shape); then sigma0 * noise + (1 - sigma0) * x_T
+            noise = noise.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            lf = self.latent_format
+            x_T = torch.empty_like(noise)
+            for b in range(B):
+                ops.vae_sample_latent(hidden, noise[b:b + 1], lf.shift_factor, lf.scale_factor, out=x_T[b:b + 1])
+            x = ops.axpby(noise, x_T, s0, 1.0 - s0)
         extra_args = {"conditioning": conditioning, "cfg_weight": cfg_weight,
                       "pooled_conditioning": pooled_conditioning}
         latent, iter_time = sample_euler(CFGDenoiser(self), x, sigmas, extra_args=extra_args)
@@ -400,6 +445,45 @@ class DiffusionPipeline:
             sigs += [0.0]
         return np.asarray(sigs, dtype=np.float32)
 
+    def _load_image_u8(self, image) -> np.ndarray:
+        """-> uint8 (H, W, >=3) with H, W multiples of 64 (read_image's resize rule, :540-546)"""
+        from PIL import Image
+
+        if isinstance(image, (str, bytes)) or hasattr(image, "__fspath__"):
+            image = Image.open(image)
+        if isinstance(image, np.ndarray):
+            if image.dtype != np.uint8 or image.ndim != 3 or image.shape[2] < 3:
+                raise ValueError("image array must be uint8 (H, W, >=3)")
+            image = Image.fromarray(image[:, :, :3])
+        W, H = (dim - dim % 64 for dim in (image.width, image.height))
+        if W == 0 or H == 0:
+            raise ValueError(f"image {image.width}x{image.height} is smaller than 64x64")
+        if W != image.width or H != image.height:
+            image = image.resize((W, H), Image.LANCZOS)
+        arr = np.asarray(image)
+        if arr.ndim == 2:
+            raise ValueError("greyscale images are not supported (the reference indexes img[:, :, :3])")
+        return np.ascontiguousarray(arr)
+
+    def read_image(self, image_path):
+        """-> (1, H, W, 3) float32 in [-1, 1] on the host (reference :536-551)"""
+        arr = self._load_image_u8(image_path)
+        return (torch.from_numpy(arr[:, :, :3].astype(np.float32)) / 255 * 2 - 1.0).unsqueeze(0)
+
+    def _encode_image_hidden(self, image_path) -> torch.Tensor:
+        if not hasattr(self, "encoder"):
+            self.load_encoder()
+        arr = self._load_image_u8(image_path)
+        host = torch.from_numpy(arr).unsqueeze(0).pin_memory()
+        return self.encoder(host.to(self.device, non_blocking=True))       # the /255*2-1 runs in dk_image_pre
+
+    def encode_image_to_latents(self, image_path, seed):
+        """mean + exp(0.5 * clip(logvar, -30, 20)) * get_noise(seed)  (reference :586-594) -> (1, H/8, W/8, 16) fp32"""
+        hidden = self._encode_image_hidden(image_path)
+        mean_like = torch.empty((1, hidden.shape[1], hidden.shape[2], hidden.shape[3] // 2))
+        noise = self.get_noise(seed, mean_like).to(self.device)
+        return ops.vae_sample_latent(hidden, noise.contiguous(), 0.0, 1.0)
+
     def get_empty_latent(self, *shape):
         return torch.ones([1, *shape, 16], dtype=torch.float32) * 0.0609
 
@@ -443,10 +527,13 @@ class FluxPipeline(DiffusionPipeline):
         mmdit_config=None,
         weight_seed: int = 0,
         load_decoder: bool = True,
+        vae_encoder_params=None,
+        load_encoder: bool = False,
     ):
         if quantize_mmdit:
             raise NotImplementedError("4-bit MMDiT variants are SURVEY.md §8 row f4")
         self.float16_dtype = torch.bfloat16                                 # :610
+        self._vae_encoder_params, self._load_encoder = vae_encoder_params, load_encoder
         self._setup(w16, a16, shift, model_version, low_memory_mode, local_ckpt, device, params, vae_params,
                     mmdit_config, weight_seed, load_decoder)
         self.sampler = FluxSampler(shift=shift)

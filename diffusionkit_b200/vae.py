@@ -1,10 +1,13 @@
-"""VAE decoder on B200 — host-side mirror of the reference VAEDecoder
-(python/src/diffusionkit/mlx/vae.py:336-401; ResnetBlock2D :60-101, Attention :28-57, upsample_nearest :20-25).
+"""VAE decoder and encoder on B200 — host-side mirrors of the reference VAEDecoder / VAEEncoder
+(python/src/diffusionkit/mlx/vae.py:336-401 and :404-467; ResnetBlock2D :60-101, Attention :28-57,
+upsample_nearest :20-25, EncoderDecoderBlock2D :103-148).
 
 Same parameter names as the reference module tree.  Kernels (csrc/):
   conv 3x3        : tcgen05 implicit GEMM, the 9 taps are shifted 4-D TMA boxes (zero fill = padding), bias and the
                     ResNet skip fused in the epilogue
   GroupNorm(32)   : two-stage fp32 statistics + fused normalise/affine/SiLU
+  conv 3x3 / 2    : same kernel, the TMA box walks the input with element stride 2 (zero fill = the reference's
+                    bottom/right pad, vae.py:142-144)
   mid attention   : q/k/v/out projections and both S=HW x HW matmuls on the tcgen05 GEMM (scores materialised like the
                     reference, vae.py:49-52; V consumed as an MN-major operand), fp32 row softmax
 """
@@ -17,7 +20,7 @@ import torch
 
 from . import ops
 from ._lib import DkError
-from .config import VAEDecoderConfig
+from .config import VAEDecoderConfig, VAEEncoderConfig
 
 
 def _pad_dim(t: torch.Tensor, dim: int, to: int) -> torch.Tensor:
@@ -28,24 +31,21 @@ def _pad_dim(t: torch.Tensor, dim: int, to: int) -> torch.Tensor:
     return torch.cat([t, torch.zeros(shape, dtype=t.dtype, device=t.device)], dim=dim).contiguous()
 
 
-class VAEDecoder:
-    def __init__(self, params: Dict[str, torch.Tensor], config: VAEDecoderConfig = VAEDecoderConfig(), device=None):
+class _VAEBlocks:
+    """Parameter handling and the building blocks the decoder and the encoder share."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], config, device=None):
+        who = type(self).__name__
         any_p = next(iter(params.values()))
         self.device = torch.device(device) if device is not None else any_p.device
         if self.device.type != "cuda":
-            raise DkError("VAEDecoder: parameters must live on a CUDA device (no CPU fallback)")
+            raise DkError(f"{who}: parameters must live on a CUDA device (no CPU fallback)")
         self.dtype = any_p.dtype
         if self.dtype not in (torch.bfloat16, torch.float16):
-            raise DkError(f"VAEDecoder: weights must be bf16 or fp16, got {self.dtype}")
+            raise DkError(f"{who}: weights must be bf16 or fp16, got {self.dtype}")
         self.config = config
         self.groups = config.resnet_groups
         self.p = {k: v.to(device=self.device, dtype=self.dtype).contiguous() for k, v in params.items()}
-        # the tensor-core conv wants Cin % 64 == 0 and Cout % 8 == 0: zero-pad the two odd layers once
-        self.cin_pad = 64
-        self.p["conv_in.weight"] = _pad_dim(self.p["conv_in.weight"], 3, self.cin_pad)
-        self.cout_pad = 8
-        self.p["conv_out.weight"] = _pad_dim(self.p["conv_out.weight"], 0, self.cout_pad)
-        self.p["conv_out.bias"] = _pad_dim(self.p["conv_out.bias"], 0, self.cout_pad)
         self._gn_ws = None
 
     # ------------------------------------------------------------------ building blocks
@@ -93,6 +93,23 @@ class VAEDecoder:
         out = self._lin(o, name + ".out_proj", res=x.reshape(B * S, C))
         return out.reshape(B, H, W, C)
 
+    def _pad_channels(self, x, to):
+        B, H, W, C = x.shape
+        xin = torch.zeros((B, H, W, to), dtype=self.dtype, device=self.device)
+        ops.copy_rows(x, xin, B * H * W, 1, C, to // C, 0, 1, 0)
+        return xin
+
+
+class VAEDecoder(_VAEBlocks):
+    def __init__(self, params: Dict[str, torch.Tensor], config: VAEDecoderConfig = VAEDecoderConfig(), device=None):
+        super().__init__(params, config, device)
+        # the tensor-core conv wants Cin % 64 == 0 and Cout % 8 == 0: zero-pad the two odd layers once
+        self.cin_pad = 64
+        self.p["conv_in.weight"] = _pad_dim(self.p["conv_in.weight"], 3, self.cin_pad)
+        self.cout_pad = 8
+        self.p["conv_out.weight"] = _pad_dim(self.p["conv_out.weight"], 0, self.cout_pad)
+        self.p["conv_out.bias"] = _pad_dim(self.p["conv_out.bias"], 0, self.cout_pad)
+
     # ------------------------------------------------------------------ forward
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """x (B, H, W, 16) NHWC -> (B, 8H, 8W, 3) NHWC view (channel stride 1, pixel stride 8)."""
@@ -100,9 +117,7 @@ class VAEDecoder:
             raise ValueError(f"VAEDecoder expects NHWC rank-4 input, got rank {x.dim()}")
         B, H, W, C = x.shape
         x = x.to(device=self.device, dtype=self.dtype).contiguous()
-        xin = torch.zeros((B, H, W, self.cin_pad), dtype=self.dtype, device=self.device)
-        ops.copy_rows(x, xin, B * H * W, 1, C, self.cin_pad // C, 0, 1, 0)
-        h = self._conv(xin, "conv_in")
+        h = self._conv(self._pad_channels(x, self.cin_pad), "conv_in")
         h = self._resnet(h, "mid_blocks.0")
         h = self._attention(h, "mid_blocks.1")
         h = self._resnet(h, "mid_blocks.2")
@@ -115,3 +130,45 @@ class VAEDecoder:
         h = self._gn(h, "conv_norm_out", True)
         out = self._conv(h, "conv_out")                               # (B, 8H, 8W, 8) — 3 real channels
         return out[..., : self.config.out_channels]
+
+
+class VAEEncoder(_VAEBlocks):
+    """reference VAEEncoder (vae.py:404-467).  Input: the uint8 image itself — read_image's `/255*2-1`
+    (__init__.py:548-549) is fused into the channel-padding kernel.  The reference keeps the encoder in fp32
+    (load_vae_encoder(float16=False), __init__.py:116); here it runs in the pipeline's 16-bit activation type with fp32
+    accumulation."""
+
+    def __init__(self, params: Dict[str, torch.Tensor], config: VAEEncoderConfig = VAEEncoderConfig(), device=None):
+        super().__init__(params, config, device)
+        self.cin_pad = 64
+        self.p["conv_in.weight"] = _pad_dim(self.p["conv_in.weight"], 3, self.cin_pad)
+
+    def encode_hidden(self, x16: torch.Tensor) -> torch.Tensor:
+        """x16 (B, H, W, cin_pad) 16-bit NHWC in [-1, 1] -> hidden (B, H/8, W/8, 32) = (mean | logvar)"""
+        h = self._conv(x16, "conv_in")
+        n = len(self.config.block_out_channels)
+        for i in range(n):
+            for l in range(self.config.layers_per_block):
+                h = self._resnet(h, f"down_blocks.{i}.resnets.{l}")
+            if f"down_blocks.{i}.downsample.weight" in self.p:        # pad (0,1),(0,1) + stride 2 (vae.py:142-144)
+                h = ops.conv3x3_s2(h, self.p[f"down_blocks.{i}.downsample.weight"],
+                                   self.p[f"down_blocks.{i}.downsample.bias"])
+        h = self._resnet(h, "mid_blocks.0")
+        h = self._attention(h, "mid_blocks.1")
+        h = self._resnet(h, "mid_blocks.2")
+        h = self._gn(h, "conv_norm_out", True)
+        return self._conv(h, "conv_out")
+
+    def __call__(self, image: torch.Tensor) -> torch.Tensor:
+        """image: uint8 NHWC (B, H, W, >=3) on the device, or a 16/32-bit float NHWC (B, H, W, 3) already in [-1, 1]."""
+        if image.dim() != 4:
+            raise ValueError(f"VAEEncoder expects NHWC rank-4 input, got rank {image.dim()}")
+        if image.shape[1] % 8 or image.shape[2] % 8:
+            raise ValueError(f"VAEEncoder: image size {tuple(image.shape[1:3])} must be a multiple of 8")
+        image = image.to(self.device)
+        if image.dtype == torch.uint8:
+            x16 = ops.image_pre(image.contiguous(), self.dtype, self.cin_pad)
+        else:
+            x16 = torch.zeros((*image.shape[:3], self.cin_pad), dtype=self.dtype, device=self.device)
+            x16[..., :3] = image[..., :3].to(self.dtype)
+        return self.encode_hidden(x16)

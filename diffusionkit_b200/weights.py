@@ -12,7 +12,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from .config import MMDiTConfig, PositionalEncoding, VAEDecoderConfig
+from .config import MMDiTConfig, PositionalEncoding, VAEDecoderConfig, VAEEncoderConfig
 
 # kind: "w" matrix/conv weight (fan_in = prod(shape[1:])), "b" bias, "g" norm gain, "e" embedding table
 Spec = Tuple[str, Tuple[int, ...], str]
@@ -66,37 +66,63 @@ def mmdit_param_specs(cfg: MMDiTConfig) -> List[Spec]:
     return specs
 
 
-def vae_decoder_param_specs(cfg: VAEDecoderConfig = VAEDecoderConfig()) -> List[Spec]:
-    specs: List[Spec] = []
-    boc = list(cfg.block_out_channels)
+class _VaeSpecBuilder:
+    def __init__(self):
+        self.specs: List[Spec] = []
 
-    def conv(name, cout, cin):
-        specs.append((name + ".weight", (cout, 3, 3, cin), "w"))
-        specs.append((name + ".bias", (cout,), "b"))
+    def conv(self, name, cout, cin):
+        self.specs.append((name + ".weight", (cout, 3, 3, cin), "w"))
+        self.specs.append((name + ".bias", (cout,), "b"))
 
-    def gn(name, c):
-        specs.append((name + ".weight", (c,), "g"))
-        specs.append((name + ".bias", (c,), "b"))
+    def gn(self, name, c):
+        self.specs.append((name + ".weight", (c,), "g"))
+        self.specs.append((name + ".bias", (c,), "b"))
 
-    def lin(name, cout, cin):
-        specs.append((name + ".weight", (cout, cin), "w"))
-        specs.append((name + ".bias", (cout,), "b"))
+    def lin(self, name, cout, cin):
+        self.specs.append((name + ".weight", (cout, cin), "w"))
+        self.specs.append((name + ".bias", (cout,), "b"))
 
-    def resnet(name, cin, cout):
-        gn(name + ".norm1", cin)
-        conv(name + ".conv1", cout, cin)
-        gn(name + ".norm2", cout)
-        conv(name + ".conv2", cout, cout)
+    def resnet(self, name, cin, cout):
+        self.gn(name + ".norm1", cin)
+        self.conv(name + ".conv1", cout, cin)
+        self.gn(name + ".norm2", cout)
+        self.conv(name + ".conv2", cout, cout)
         if cin != cout:
-            lin(name + ".conv_shortcut", cout, cin)
+            self.lin(name + ".conv_shortcut", cout, cin)
 
+    def mid(self, top):
+        self.resnet("mid_blocks.0", top, top)
+        self.gn("mid_blocks.1.group_norm", top)
+        for n in ("query_proj", "key_proj", "value_proj", "out_proj"):
+            self.lin("mid_blocks.1." + n, top, top)
+        self.resnet("mid_blocks.2", top, top)
+
+
+def vae_encoder_param_specs(cfg: VAEEncoderConfig = VAEEncoderConfig()) -> List[Spec]:
+    """reference VAEEncoder module tree (mlx/vae.py:404-451)"""
+    b = _VaeSpecBuilder()
+    boc = list(cfg.block_out_channels)
+    b.conv("conv_in", boc[0], cfg.in_channels)
+    channels = [boc[0]] + boc
+    for i, (cin, cout) in enumerate(zip(channels, channels[1:])):
+        for l in range(cfg.layers_per_block):
+            b.resnet(f"down_blocks.{i}.resnets.{l}", cin if l == 0 else cout, cout)
+        if i < len(boc) - 1:
+            b.conv(f"down_blocks.{i}.downsample", cout, cout)
+    b.mid(boc[-1])
+    b.gn("conv_norm_out", boc[-1])
+    b.conv("conv_out", cfg.out_channels, boc[-1])
+    return b.specs
+
+
+def vae_decoder_param_specs(cfg: VAEDecoderConfig = VAEDecoderConfig()) -> List[Spec]:
+    b = _VaeSpecBuilder()
+    specs = b.specs
+    conv, gn, resnet = b.conv, b.gn, b.resnet
+    boc = list(cfg.block_out_channels)
     top = boc[-1]
     conv("conv_in", top, cfg.in_channels)
-    resnet("mid_blocks.0", top, top)
-    gn("mid_blocks.1.group_norm", top)
-    for n in ("query_proj", "key_proj", "value_proj", "out_proj"):
-        lin("mid_blocks.1." + n, top, top)
-    resnet("mid_blocks.2", top, top)
+    b.mid(top)
     channels = list(reversed(boc))
     channels = [channels[0]] + channels
     n_blocks = len(boc)

@@ -150,6 +150,16 @@ int dk_sampler_step(dk_ctx* ctx, int dtype, float* x, const void* xin, const voi
                     float sigma_next, float cfg_weight, void* stream);
 /* y = x * a + b (fp32): latent_format.process_out (__init__.py:732-733) and noise scaling (sampler.py:41-42) */
 int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, float a, float b, void* stream);
+/* read_image (__init__.py:536-551): uint8 [pixels, src_channels >= 3] -> 16-bit [pixels, cpad]; channels 0..2 =
+ * u8 / 255 * 2 - 1, the padding channels are zero */
+int dk_image_pre(dk_ctx* ctx, int dtype, const uint8_t* img, void* out, long long pixels, int src_channels, int cpad,
+                 void* stream);
+/* out = a * x + b * y (fp32): img2img noise scaling sigma * noise + (1 - sigma) * latent (sampler.py:41-42) */
+int dk_axpby_f32(dk_ctx* ctx, const float* x, const float* y, float* out, long long n, float a, float b, void* stream);
+/* VAE-encoder posterior sample + process_in: hidden [pixels, 2C] 16-bit = (mean | logvar);
+ * out = ((mean + exp(0.5 * clip(logvar, -30, 20)) * noise) - shift) * scale   (__init__.py:586-594, :729-730) */
+int dk_vae_sample_latent(dk_ctx* ctx, int dtype, const void* hidden, const float* noise, float* out, long long pixels,
+                         int C, float shift, float scale, void* stream);
 /* fp32 <-> 16-bit casts */
 int dk_cast_f32_to_16(dk_ctx* ctx, int dtype, const float* x, void* y, long long n, void* stream);
 int dk_cast_16_to_f32(dk_ctx* ctx, int dtype, const void* x, float* y, long long n, void* stream);
@@ -172,6 +182,11 @@ int dk_groupnorm_apply(dk_ctx* ctx, int dtype, const void* x, void* y, const flo
  *     (the ResnetBlock2D skip, vae.py:99).  replaces nn.Conv2d 3x3 (vae.py:73-81,134-136,349-351,384) */
 int dk_conv3x3(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, const void* res, void* out,
                int B, int H, int W, int Cin, int Cout, void* stream);
+/* 3x3 convolution with stride 2 and mlx's (0,1),(0,1) bottom/right zero padding — the VAE encoder's downsample
+ * (vae.py:130-132,142-144).  x [B,H,W,Cin] (H, W even) -> out [B,H/2,W/2,Cout].  Same TMA implicit GEMM; the tap tile is
+ * a 4-D box traversed with element stride 2. */
+int dk_conv3x3_s2(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, void* out, int B, int H, int W,
+                  int Cin, int Cout, void* stream);
 /* nearest 2x upsample NHWC (vae.py:20-25) */
 int dk_upsample_nearest2x(dk_ctx* ctx, int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* row softmax in place: x[r, :n] = softmax(scale * x[r, :n]); fp32 math, 16-bit storage (vae.py:49-52) */

@@ -1,7 +1,8 @@
 """ORACLE (test infrastructure — never imported by the product path).
 
-CPU PyTorch fp32 restatement of the reference VAE decoder (python/src/diffusionkit/mlx/vae.py:20-149, 336-401) and of
-decode_latents_to_image (mlx/__init__.py:581-584).
+CPU PyTorch fp32 restatement of the reference VAE decoder and encoder (python/src/diffusionkit/mlx/vae.py:20-149,
+336-401, 404-467), of decode_latents_to_image (mlx/__init__.py:581-584) and of read_image / encode_image_to_latents
+(mlx/__init__.py:536-551, 586-594).
 
 PARITY UNPINNED: MLX cannot run here and the repo holds no golden tensors for this path (see oracle/mmdit_ref.py).
 
@@ -26,6 +27,14 @@ def conv3x3(x, w, b, dt=None):
     return _r(y.permute(0, 2, 3, 1), dt)
 
 
+def conv3x3_s2(x, w, b, dt=None):
+    """EncoderDecoderBlock2D downsample (vae.py:142-144): mx.pad [(0,0),(0,1),(0,1),(0,0)] then Conv2d(k=3, stride 2,
+    padding 0)"""
+    xp = F.pad(x.permute(0, 3, 1, 2), (0, 1, 0, 1))
+    y = F.conv2d(xp, w.float().permute(0, 3, 1, 2), b.float(), stride=2)
+    return _r(y.permute(0, 2, 3, 1), dt)
+
+
 def group_norm(x, w, b, groups=32, eps=1e-5, dt=None):
     """mlx nn.GroupNorm(32, C, pytorch_compatible=True), default eps 1e-5 (vae.py:34,72,78; quirk Q7)"""
     y = F.group_norm(x.permute(0, 3, 1, 2), groups, w.float(), b.float(), eps)
@@ -37,9 +46,9 @@ def upsample_nearest(x, scale=2):
     return x.repeat_interleave(scale, dim=1).repeat_interleave(scale, dim=2)
 
 
-class VAEDecoderRef:
-    def __init__(self, params: Dict[str, torch.Tensor], act_dtype: Optional[torch.dtype] = None,
-                 block_out_channels=(128, 256, 512, 512), layers_per_block: int = 3, groups: int = 32):
+class _VAEBlocksRef:
+    def __init__(self, params: Dict[str, torch.Tensor], act_dtype: Optional[torch.dtype],
+                 block_out_channels, layers_per_block: int, groups: int):
         self.p = params
         self.dt = act_dtype
         self.boc = list(block_out_channels)
@@ -81,6 +90,12 @@ class VAEDecoderRef:
         y = self._lin(y, name + ".out_proj")
         return _r(x + y, self.dt)
 
+
+class VAEDecoderRef(_VAEBlocksRef):
+    def __init__(self, params: Dict[str, torch.Tensor], act_dtype: Optional[torch.dtype] = None,
+                 block_out_channels=(128, 256, 512, 512), layers_per_block: int = 3, groups: int = 32):
+        super().__init__(params, act_dtype, block_out_channels, layers_per_block, groups)
+
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
         """VAEDecoder.__call__ (vae.py:386-401): x (B, H, W, 16) -> (B, 8H, 8W, 3)"""
         x = self._conv(_r(x.float(), self.dt), "conv_in")
@@ -96,6 +111,41 @@ class VAEDecoderRef:
         x = self._gn(x, "conv_norm_out")
         x = _r(F.silu(x), self.dt)
         return self._conv(x, "conv_out")
+
+
+class VAEEncoderRef(_VAEBlocksRef):
+    def __init__(self, params: Dict[str, torch.Tensor], act_dtype: Optional[torch.dtype] = None,
+                 block_out_channels=(128, 256, 512, 512), layers_per_block: int = 2, groups: int = 32):
+        super().__init__(params, act_dtype, block_out_channels, layers_per_block, groups)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """VAEEncoder.__call__ (vae.py:453-467): x (B, H, W, 3) in [-1, 1] -> (B, H/8, W/8, 32) = (mean | logvar)"""
+        x = self._conv(_r(x.float(), self.dt), "conv_in")
+        for i in range(len(self.boc)):
+            for l in range(self.layers):
+                x = self.resnet(x, f"down_blocks.{i}.resnets.{l}")
+            name = f"down_blocks.{i}.downsample"
+            if (name + ".weight") in self.p:
+                x = conv3x3_s2(x, self.p[name + ".weight"], self.p[name + ".bias"], self.dt)
+        x = self.resnet(x, "mid_blocks.0")
+        x = self.attention(x, "mid_blocks.1")
+        x = self.resnet(x, "mid_blocks.2")
+        x = self._gn(x, "conv_norm_out")
+        x = _r(F.silu(x), self.dt)
+        return self._conv(x, "conv_out")
+
+
+def read_image_array(img_u8: torch.Tensor) -> torch.Tensor:
+    """read_image after PIL (mlx/__init__.py:548-551): uint8 (H, W, >=3) -> (1, H, W, 3) fp32 in [-1, 1]"""
+    return ((img_u8[:, :, :3].to(torch.float32) / 255) * 2 - 1.0).unsqueeze(0)
+
+
+def encode_image_to_latents(encoder: VAEEncoderRef, image: torch.Tensor, noise: torch.Tensor) -> torch.Tensor:
+    """mlx/__init__.py:586-594 with the seeded draw passed in: mean + exp(0.5 * clip(logvar, -30, 20)) * noise"""
+    hidden = encoder(image)
+    mean, logvar = hidden.split(hidden.shape[-1] // 2, dim=-1)
+    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+    return mean + std * noise.float()
 
 
 def decode_latents_to_image(decoder: VAEDecoderRef, latent: torch.Tensor) -> torch.Tensor:

@@ -183,6 +183,55 @@ def check_conv3x3():
     return out
 
 
+def _conv_s2_case(B, H, W, Cin, Cout, dtype, name=""):
+    x = _rand((B, H, W, Cin), dtype)
+    w = _rand((Cout, 3, 3, Cin), dtype, 1 / math.sqrt(9 * Cin))
+    b = _rand((Cout,), dtype, 0.5)
+    # reference downsample: pad bottom/right by one, then 3x3 stride 2 without padding (mlx/vae.py:142-144)
+    xp = torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = torch.nn.functional.conv2d(xp, w.float().permute(0, 3, 1, 2), b.float(), stride=2).permute(0, 2, 3, 1)
+    got = ops.conv3x3_s2(x, w, bias=b)
+    assert got.shape == (B, H // 2, W // 2, Cout)
+    return _assert_close(name, got, ref, 4e-3)
+
+
+def check_conv3x3_s2():
+    """the encoder's stride-2 downsample: same implicit-GEMM kernel, TMA box with element stride 2"""
+    _setup()
+    out = {}
+    out["32x32"] = _conv_s2_case(2, 32, 32, 64, 64, torch.bfloat16, name="convs2_32x32")          # TW=16, TH=8
+    out["16x64"] = _conv_s2_case(1, 16, 64, 128, 128, torch.bfloat16, name="convs2_16x64")        # TW=32, TH=4
+    out["24x40_ragged"] = _conv_s2_case(2, 24, 40, 64, 72, torch.bfloat16, name="convs2_24x40")   # TW=128 ragged
+    out["64x512"] = _conv_s2_case(1, 64, 512, 128, 128, torch.bfloat16, name="convs2_64x512")     # box 256 wide
+    out["fp16"] = _conv_s2_case(1, 32, 32, 64, 16, torch.float16, name="convs2_fp16")
+    return out
+
+
+def check_img2img_kernels():
+    """dk_image_pre, dk_vae_sample_latent, dk_axpby_f32 (read_image / posterior sample / noise_scaling)"""
+    _setup()
+    out = {}
+    for dt in (torch.bfloat16, torch.float16):
+        for cs in (3, 4):
+            img = torch.randint(0, 256, (2, 8, 12, cs), dtype=torch.uint8, device=DEV)
+            got = ops.image_pre(img, dt, 64)
+            ref = torch.zeros((2, 8, 12, 64), dtype=torch.float32, device=DEV)
+            ref[..., :3] = img[..., :3].float() / 255 * 2 - 1.0
+            assert torch.equal(got, ref.to(dt)), f"image_pre {dt} {cs}"
+    hidden = _rand((1, 8, 8, 32), torch.bfloat16, 2.0)
+    hidden[0, 0, 0, 16] = 50.0       # logvar clipped at 20
+    hidden[0, 0, 1, 16] = -80.0      # ... and at -30
+    noise = torch.randn((1, 8, 8, 16), device=DEV)
+    mean, logvar = hidden.float().split(16, dim=-1)
+    z = mean + torch.exp(0.5 * logvar.clamp(-30.0, 20.0)) * noise
+    out["sample"] = _assert_close("vae_sample", ops.vae_sample_latent(hidden, noise, 0.0, 1.0), z, 1e-5)
+    out["sample_in"] = _assert_close("vae_sample_in", ops.vae_sample_latent(hidden, noise, 0.1159, 0.3611),
+                                     (z - 0.1159) * 0.3611, 1e-5)
+    a, b = torch.randn(1000, device=DEV), torch.randn(1000, device=DEV)
+    out["axpby"] = _assert_close("axpby", ops.axpby(a, b, 0.7, 0.3), 0.7 * a + 0.3 * b, 1e-6)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attention_case(B, S, heads, d, dtype, split=None, name=""):
     h = heads * d
@@ -535,7 +584,7 @@ def check_error_paths():
 ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
     check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
-    check_gemm_pair_kernel, check_conv3x3,
+    check_gemm_pair_kernel, check_conv3x3, check_conv3x3_s2, check_img2img_kernels,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
     check_attention_v1_kernel, check_attention_v2_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,

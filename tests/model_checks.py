@@ -14,11 +14,13 @@ import torch
 
 import diffusionkit_b200 as dk
 from diffusionkit_b200 import ops
-from diffusionkit_b200.config import VAEDecoderConfig, tiny_flux_config, tiny_sd3_config
-from diffusionkit_b200.weights import init_params, mmdit_param_specs, vae_decoder_param_specs
+from diffusionkit_b200.config import VAEDecoderConfig, VAEEncoderConfig, tiny_flux_config, tiny_sd3_config
+from diffusionkit_b200.weights import (init_params, mmdit_param_specs, vae_decoder_param_specs,
+                                       vae_encoder_param_specs)
 from oracle import sampler_ref as sr
 from oracle.mmdit_ref import MMDiTRef
-from oracle.vae_ref import VAEDecoderRef, decode_latents_to_image, to_uint8
+from oracle.vae_ref import (VAEDecoderRef, VAEEncoderRef, decode_latents_to_image, encode_image_to_latents,
+                            read_image_array, to_uint8)
 from tests.oracle_bridge import ref_config
 
 DEV = "cuda:0"
@@ -107,6 +109,102 @@ def check_vae_decode_tiny():
 
 def check_vae_decode_batch_fp16():
     return _vae_case(torch.float16, 2, (8, 12), 40.0)
+
+
+def _test_image(H, W, seed=5):
+    """a smooth synthetic RGB picture (low-frequency sinusoids + a little noise), uint8 (H, W, 3)"""
+    rng = np.random.RandomState(seed)
+    yy, xx = np.meshgrid(np.linspace(0, 1, H), np.linspace(0, 1, W), indexing="ij")
+    chans = [0.5 + 0.4 * np.sin(2 * np.pi * (a * xx + b * yy) + c) for a, b, c in rng.uniform(0.5, 3.0, (3, 3))]
+    img = np.stack(chans, axis=-1) + 0.03 * rng.randn(H, W, 3)
+    return (np.clip(img, 0, 1) * 255).astype(np.uint8)
+
+
+def _vae_encode_case(dtype, B, size, tol):
+    ep32 = init_params(vae_encoder_param_specs(VAEEncoderConfig()), seed=9, dtype=torch.float32)
+    ep16 = {k: v.to(dtype) for k, v in ep32.items()}
+    imgs = torch.from_numpy(np.stack([_test_image(size[0], size[1], seed=5 + i) for i in range(B)]))
+    want = torch.cat([VAEEncoderRef({k: v.float() for k, v in ep16.items()})(read_image_array(im)) for im in imgs])
+    enc = dk.VAEEncoder({k: v.to(DEV) for k, v in ep16.items()})
+    got = enc(imgs.to(DEV))
+    torch.cuda.synchronize()
+    assert got.shape == want.shape == (B, size[0] // 8, size[1] // 8, 32)
+    r = rel_l2(got, want)
+    assert r <= tol, f"vae encoder hidden rel_l2 {r:.3e}"
+    again = enc(imgs.to(DEV))
+    assert torch.equal(got, again), "encoder is not deterministic"
+    return {"hidden_rel_l2": r}
+
+
+def check_vae_encode_tiny():
+    return _vae_encode_case(torch.bfloat16, 1, (64, 64), 3e-2)
+
+
+def check_vae_encode_batch_fp16():
+    return _vae_encode_case(torch.float16, 2, (64, 128), 5e-3)
+
+
+def check_pipeline_img2img():
+    """image -> VAE encoder -> posterior sample -> process_in -> trimmed schedule -> Euler loop, vs the oracle
+    (reference denoise_latents :270-285 + encode_image_to_latents :586-594); then generate_image on a PNG file whose
+    size is not a multiple of 64 (read_image's LANCZOS resize rule)."""
+    import tempfile
+
+    from PIL import Image
+
+    cfg, dtype, steps, shift, T = tiny_flux_config(), torch.bfloat16, 4, 1.0, 16
+    p16 = {k: v.to(dtype) for k, v in init_params(mmdit_param_specs(cfg), seed=7, dtype=torch.float32).items()}
+    vp16 = {k: v.to(dtype) for k, v in init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=8,
+                                                    dtype=torch.float32).items()}
+    ep16 = {k: v.to(dtype) for k, v in init_params(vae_encoder_param_specs(VAEEncoderConfig()), seed=9,
+                                                    dtype=torch.float32).items()}
+    pipe = dk.FluxPipeline(w16=True, a16=True, shift=shift, mmdit_config=cfg,
+                           params={k: v.to(DEV) for k, v in p16.items()},
+                           vae_params={k: v.to(DEV) for k, v in vp16.items()},
+                           vae_encoder_params={k: v.to(DEV) for k, v in ep16.items()})
+    assert not hasattr(pipe, "encoder")                      # built on first use
+    img = _test_image(64, 128)
+    H, W = 8, 16
+    seeds, denoise = [11, 12], 0.5
+    n = len(seeds)
+    cond, pooled = pipe.synthetic_text_embeddings(n_images=n, text_len=T)
+    latent, iter_time = pipe.denoise_latents(cond, pooled, num_steps=steps, cfg_weight=0.0, latent_size=(2, 2),
+                                             seed=seeds, image_path=img, denoise=denoise)
+    assert latent.shape == (n, H, W, 16) and len(iter_time) == steps - int(steps * (1 - denoise))
+    sampler = sr.FluxSamplerRef(shift)
+    sig = sr.get_sigmas(sampler, steps)[int(steps * (1 - denoise)):]
+    enc_ref = VAEEncoderRef({k: v.float() for k, v in ep16.items()})
+    image = read_image_array(torch.from_numpy(img))
+    outs, zs = [], []
+    for i, s in enumerate(seeds):
+        ref = MMDiTRef(ref_config(cfg), {k: v.float() for k, v in p16.items()})
+        noise = sr.get_noise(s, H, W)
+        z = encode_image_to_latents(enc_ref, image, noise)
+        zs.append(z)
+        x_T = (z - 0.1159) * 0.3611                                        # FluxLatentFormat.process_in
+        x0 = sampler.noise_scaling(float(sig[0]), noise, x_T)
+        x = sr.sample_euler(lambda xin, c, t: ref(xin, c, t), ref.cache_modulation_params, x0, sig,
+                            cond[[i]].float(), pooled[[i]].float(), 0.0, dtype)
+        outs.append(sr.process_out(x, "flux"))
+    r = rel_l2(latent, torch.cat(outs))
+    assert r <= 5e-2, f"img2img final latent rel_l2 {r:.3e}"
+    z_got = pipe.encode_image_to_latents(img, seeds[0])
+    rz = rel_l2(z_got, zs[0])
+    assert rz <= 3e-2, f"encode_image_to_latents rel_l2 {rz:.3e}"
+    # denoise = 1.0 with an image still starts from the image-derived x_T (sigma0 = 1 -> pure noise): equals txt2img
+    full, _ = pipe.denoise_latents(cond, pooled, num_steps=steps, seed=seeds, image_path=img, denoise=1.0)
+    plain, _ = pipe.denoise_latents(cond, pooled, num_steps=steps, seed=seeds, latent_size=(H, W))
+    assert torch.equal(full, plain)
+    # file path + resize rule: 100 x 150 -> 64 x 128
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "in.png")
+        Image.fromarray(_test_image(100, 150)).save(path)
+        ri = pipe.read_image(path)
+        assert tuple(ri.shape) == (1, 64, 128, 3) and float(ri.min()) >= -1.0 and float(ri.max()) <= 1.0
+        out, log = pipe.generate_image("", num_steps=steps, seed=seeds[0], verbose=False, conditioning=cond[[0]],
+                                       pooled_conditioning=pooled[[0]], image_path=path, denoise=0.75)
+    assert out.size == (128, 64) and len(log["denoising"]["iter_time"]) == 3
+    return {"latent_rel_l2": r, "posterior_rel_l2": rz}
 
 
 def _pipeline_case(kind):
@@ -263,5 +361,6 @@ def check_full_size_vae_properties():
 
 
 ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
-              check_vae_decode_tiny, check_vae_decode_batch_fp16, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
+              check_vae_decode_tiny, check_vae_decode_batch_fp16, check_vae_encode_tiny, check_vae_encode_batch_fp16,
+              check_pipeline_img2img, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
               check_pipeline_errors, check_pipeline_local_ckpt, check_full_size_flux_properties, check_full_size_vae_properties]

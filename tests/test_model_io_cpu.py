@@ -9,7 +9,8 @@ import torch
 
 from diffusionkit_b200 import model_io
 from diffusionkit_b200.config import VAEDecoderConfig, tiny_flux_config, tiny_sd3_config
-from diffusionkit_b200.weights import init_params, mmdit_param_specs, vae_decoder_param_specs
+from diffusionkit_b200.weights import (init_params, mmdit_param_specs, vae_decoder_param_specs,
+                                       vae_encoder_param_specs)
 
 
 def _flux_upstream(params, cfg):
@@ -132,6 +133,7 @@ def _vae_upstream(params, prefix="first_stage_model.decoder."):
         else:
             k = k.replace("up_blocks.", "up.").replace(".resnets.", ".block.").replace(".conv_shortcut.", ".nin_shortcut.")
             k = k.replace(".upsample.", ".upsample.conv.")
+            k = k.replace("down_blocks.", "down.").replace(".downsample.", ".downsample.conv.")
             if leaf == "weight" and t.dim() == 4:
                 v = oihw(t)
             elif leaf == "weight" and "nin_shortcut" in k:
@@ -157,6 +159,23 @@ def test_vae_decoder_checkpoint_roundtrip(tmp_path):
     model_io.check_against_specs(got, specs)
     for name, t in params.items():
         assert torch.equal(got[name], t), name
+
+
+def test_vae_encoder_checkpoint_roundtrip():
+    from diffusionkit_b200.config import VAEEncoderConfig
+
+    specs = vae_encoder_param_specs(VAEEncoderConfig())
+    params = init_params(specs, seed=8, dtype=torch.float32)
+    up = _vae_upstream(params, prefix="first_stage_model.encoder.")
+    assert "first_stage_model.encoder.down.2.downsample.conv.weight" in up
+    assert "first_stage_model.encoder.down.3.downsample.conv.weight" not in up
+    assert up["first_stage_model.encoder.down.1.block.0.nin_shortcut.weight"].shape == (256, 128, 1, 1)
+    up["first_stage_model.decoder.conv_in.bias"] = torch.zeros(3)          # the decoder half of the file is skipped
+    got = model_io.vae_encoder_checkpoint_to_params(up)
+    model_io.check_against_specs(got, specs)
+    for name, t in params.items():
+        assert torch.equal(got[name], t), name
+    assert got["conv_out.weight"].shape == (32, 3, 3, 512)
 
 
 def test_unknown_keys_and_shape_mismatch_are_reported():
