@@ -62,6 +62,7 @@ SIGNATURES = {
     "dk_sampler_prepare": (i32, [vp, i32, vp, vp, i64, i32, vp]),
     "dk_sampler_step": (i32, [vp, i32, vp, vp, vp, i64, f32, f32, f32, vp]),
     "dk_axpb_f32": (i32, [vp, vp, vp, i64, f32, f32, vp]),
+    "dk_dequant_q4": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]),
     "dk_image_pre": (i32, [vp, i32, vp, vp, i64, i32, i32, vp]),
     "dk_axpby_f32": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),
     "dk_vae_sample_latent": (i32, [vp, i32, vp, vp, vp, i64, i32, f32, f32, vp]),

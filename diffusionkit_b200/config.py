@@ -100,15 +100,29 @@ class VAEEncoderConfig:
 MODEL_CONFIGS = {
     "argmaxinc/mlx-stable-diffusion-3-medium": SD3_2b,
     "argmaxinc/mlx-FLUX.1-schnell": FLUX_SCHNELL,
+    "argmaxinc/mlx-FLUX.1-schnell-4bit-quantized": FLUX_SCHNELL,
     "argmaxinc/mlx-FLUX.1-dev": FLUX_SCHNELL,  # quirk Q1
+    "argmaxinc/mlx-stable-diffusion-3.5-large": SD3_8b,
+    "argmaxinc/mlx-stable-diffusion-3.5-large-4bit-quantized": SD3_8b,
 }
 
 # T5 sequence lengths (mlx/__init__.py:46-53)
 T5_MAX_LENGTH = {
     "argmaxinc/mlx-stable-diffusion-3-medium": 512,
+    "argmaxinc/mlx-stable-diffusion-3.5-large": 512,
+    "argmaxinc/mlx-stable-diffusion-3.5-large-4bit-quantized": 512,
     "argmaxinc/mlx-FLUX.1-schnell": 256,
+    "argmaxinc/mlx-FLUX.1-schnell-4bit-quantized": 256,
     "argmaxinc/mlx-FLUX.1-dev": 512,
 }
+
+
+def tiny_sd35_config(hidden: int = 128, heads: int = 2, depth: int = 2) -> MMDiTConfig:
+    """Small SD3.5-shaped config for tests: learned positional embedding + QK-RMSNorm, head dim 64, bf16 sinusoid
+    (SD3_8b keeps the dataclass default dtype, mlx/config.py:74-76)."""
+    return MMDiTConfig(num_heads=heads, depth_multimodal=depth, hidden_size_override=hidden, use_qk_norm=True,
+                       upcast_multimodal_blocks=[depth - 1], max_latent_resolution=24, pooled_text_embed_dim=64,
+                       token_level_text_embed_dim=128)
 
 
 def tiny_flux_config(hidden: int = 256, heads: int = 2, depth_mm: int = 2, depth_uni: int = 2) -> MMDiTConfig:

@@ -326,6 +326,33 @@ __global__ void axpb_kernel(const float* __restrict__ x, float* __restrict__ y, 
        i += static_cast<long long>(gridDim.x) * blockDim.x)
     y[i] = x[i] * a + b;
 }
+// MLX affine 4-bit weights (mx.quantize, group_size 64, bits 4; reference nn.quantize call sites mlx/model_io.py:728-734,
+// 772-775) -> dense 16-bit: w[n, k] = scales[n, k / group] * q[n, k] + biases[n, k / group], q = nibble (k % 8) of
+// word wq[n, k / 8] (element 0 in the low bits).  One thread = one word = 8 outputs = one 16-byte store.
+template <typename T>
+__global__ void dequant_q4_kernel(const uint32_t* __restrict__ wq, const T* __restrict__ scales,
+                                  const T* __restrict__ biases, T* __restrict__ out, long long N, int K, int group) {
+  const int wpr = K / 8;  // words per row
+  const int gpr = K / group;
+  const long long nwords = N * wpr;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nwords;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long n = i / wpr;
+    const int k0 = static_cast<int>(i - n * wpr) * 8;
+    const uint32_t w = wq[i];
+    const float sc = Half16<T>::to_f(scales[n * gpr + k0 / group]);
+    const float bi = Half16<T>::to_f(biases[n * gpr + k0 / group]);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = __fmaf_rn(sc, static_cast<float>((w >> (8 * j)) & 0xFu), bi);
+      const float b = __fmaf_rn(sc, static_cast<float>((w >> (8 * j + 4)) & 0xFu), bi);
+      o[j] = Half16<T>::pack(a, b);
+    }
+    *reinterpret_cast<uint4*>(out + n * K + k0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // read_image (reference mlx/__init__.py:536-551): uint8 [pixels, src_c >= 3] -> 16-bit [pixels, cpad], channels 0..2 =
 // u8 / 255 * 2 - 1 (fp32 arithmetic, then rounded to T), channels 3.. = 0 (the tensor-core conv wants Cin % 64 == 0)
 template <typename T>
@@ -834,6 +861,22 @@ extern "C" int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, f
   DK_REQUIRE(ctx != nullptr, "dk_axpb_f32: null ctx");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   axpb_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(x, y, n, a, b);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+extern "C" int dk_dequant_q4(dk_ctx* ctx, int dtype, const uint32_t* wq, const void* scales, const void* biases,
+                             void* out, long long N, int K, int group_size, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_dequant_q4: null ctx");
+  DK_DTYPE_OK(dtype);
+  DK_REQUIRE(N > 0 && K > 0, "dk_dequant_q4: empty weight");
+  DK_REQUIRE(group_size >= 8 && group_size % 8 == 0 && K % group_size == 0,
+             "dk_dequant_q4: K (%d) must be a multiple of group_size (%d), itself a multiple of 8", K, group_size);
+  DK_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15u) == 0, "dk_dequant_q4: out must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DK_DISPATCH(dtype, (dequant_q4_kernel<T><<<grid_for(N * (K / 8), 256, ctx->sm_count), 256, 0, stream>>>(
+                         wq, static_cast<const T*>(scales), static_cast<const T*>(biases), static_cast<T*>(out), N, K,
+                         group_size)));
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }

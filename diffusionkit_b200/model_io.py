@@ -232,6 +232,44 @@ def vae_encoder_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "encod
     return _vae_checkpoint_to_params(sd, prefix, "down")
 
 
+# ------------------------------------------------------------------------------------------------ 4-bit variants
+def is_q4_checkpoint(sd: Dict[str, Tensor]) -> bool:
+    return any(k.endswith(".scales") for k in sd)
+
+
+def preadjusted_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "") -> Dict[str, Tensor]:
+    """The `*-4bit-quantized` checkpoints were saved from the reference's own module tree, so their keys already are
+    the App. C names (behind `prefix` for the single-file SD3.5 checkpoint): keep the keys that contain the prefix and
+    strip it (reference model_io.py:733-734, 772-775 "4-bit ckpt already adjusted")."""
+    if not prefix:
+        return dict(sd)
+    return {k.replace(prefix, ""): v for k, v in sd.items() if prefix in k}
+
+
+def dequantize_q4_params(sd: Dict[str, Tensor], device, dtype: torch.dtype, group_size: int = 64) -> Dict[str, Tensor]:
+    """MLX QuantizedLinear triples (`X.weight` uint32 [N, K/8], `X.scales`, `X.biases` [N, K/64]) -> dense 16-bit
+    `X.weight` [N, K] on `device` (dk_dequant_q4).  On B200 the denoise GEMMs are tensor-pipe bound at M >= 1024 rows
+    and the dense FLUX weights are 13 % of HBM, so the 4-bit form is expanded once at load instead of inside every GEMM
+    (DESIGN.md §7).  Every other tensor is passed through (cast to `dtype` like the reference, :736-738)."""
+    from . import ops
+
+    out: Dict[str, Tensor] = {}
+    for k, v in sd.items():
+        if k.endswith((".scales", ".biases")) and (k.rsplit(".", 1)[0] + ".weight") in sd:
+            continue
+        base = k[:-7] if k.endswith(".weight") else None
+        if base is not None and (base + ".scales") in sd:
+            if v.dtype not in (torch.uint32, torch.int32):
+                raise ValueError(f"{k}: quantised weight must be uint32, got {v.dtype}")
+            wq = v.contiguous().view(torch.int32).to(device)
+            sc = sd[base + ".scales"].to(device=device, dtype=dtype).contiguous()
+            bi = sd[base + ".biases"].to(device=device, dtype=dtype).contiguous()
+            out[k] = ops.dequant_q4(wq, sc, bi, group_size)
+        else:
+            out[k] = v.to(device=device, dtype=dtype) if v.is_floating_point() else v.to(device)
+    return out
+
+
 def check_against_specs(params: Dict[str, Tensor], specs: Iterable[Tuple[str, Tuple[int, ...], str]],
                         allow_extra: Iterable[str] = ()) -> None:
     """Raise if the converted tree does not match the engine's parameter specs (names and shapes)."""

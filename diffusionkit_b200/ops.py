@@ -234,6 +234,21 @@ def axpb(x, a: float, b: float, out=None):
     return out
 
 
+def dequant_q4(wq, scales, biases, group_size: int = 64, out=None):
+    """MLX affine 4-bit weight (wq [N, K/8] uint32 stored as int32/uint32, scales/biases [N, K/group] 16-bit) ->
+    dense [N, K] in the scales' dtype"""
+    _chk16(scales, "dequant_q4.scales")
+    assert wq.dtype in (torch.int32, torch.uint32) and wq.dim() == 2 and wq.is_contiguous() and wq.is_cuda
+    assert scales.is_contiguous() and biases.is_contiguous() and biases.dtype == scales.dtype
+    N, K = wq.shape[0], wq.shape[1] * 8
+    assert tuple(scales.shape) == tuple(biases.shape) == (N, K // group_size)
+    if out is None:
+        out = torch.empty((N, K), dtype=scales.dtype, device=wq.device)
+    c = ctx(wq.device.index)
+    c.call("dk_dequant_q4", dtype_code(scales.dtype), ptr(wq), ptr(scales), ptr(biases), ptr(out), N, K, group_size)
+    return out
+
+
 def image_pre(img_u8, dtype, cpad: int = 64):
     """uint8 NHWC [B,H,W,>=3] -> 16-bit NHWC [B,H,W,cpad] in [-1, 1] (channels 3.. zero)"""
     assert img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and img_u8.dim() == 4 and img_u8.is_cuda

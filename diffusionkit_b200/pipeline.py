@@ -28,9 +28,12 @@ from .sampler import FluxSampler, ModelSamplingDiscreteFlow
 from .vae import VAEDecoder, VAEEncoder
 from .weights import init_params, mmdit_param_specs, vae_decoder_param_specs, vae_encoder_param_specs
 
-MMDIT_CKPT = {  # reference mlx/__init__.py:37-44 (quantised / SD3.5 variants: SURVEY.md §8 row f4)
+MMDIT_CKPT = {  # reference mlx/__init__.py:37-44
     "argmaxinc/mlx-stable-diffusion-3-medium": "argmaxinc/mlx-stable-diffusion-3-medium",
+    "argmaxinc/mlx-stable-diffusion-3.5-large": "argmaxinc/mlx-stable-diffusion-3.5-large",
+    "argmaxinc/mlx-stable-diffusion-3.5-large-4bit-quantized": "argmaxinc/mlx-stable-diffusion-3.5-large-4bit-quantized",
     "argmaxinc/mlx-FLUX.1-schnell": "argmaxinc/mlx-FLUX.1-schnell",
+    "argmaxinc/mlx-FLUX.1-schnell-4bit-quantized": "argmaxinc/mlx-FLUX.1-schnell-4bit-quantized",
     "argmaxinc/mlx-FLUX.1-dev": "argmaxinc/mlx-FLUX.1-dev",
 }
 
@@ -186,7 +189,20 @@ class DiffusionPipeline:
         out = {}
         if paths.get("mmdit"):
             sd = model_io.load_safetensors(paths["mmdit"])
-            if isinstance(self, FluxPipeline):
+            if self.model_version.endswith("-4bit-quantized"):
+                # saved from the reference's own module tree: names already final, Linear weights as MLX 4-bit triples
+                # (reference model_io.py:728-734 SD3.5, :772-775 FLUX); expanded to dense 16-bit once, here
+                flux = isinstance(self, FluxPipeline)
+                tree = model_io.preadjusted_checkpoint_to_params(sd, "" if flux else "model.diffusion_model.")
+                if flux:
+                    tree = {k: v for k, v in tree.items() if not k.startswith(("decoder.", "encoder."))}
+                params = model_io.dequantize_q4_params(tree, self.device, self.dtype)
+                if not flux and "vae" not in paths:
+                    for part, pref in (("vae", "first_stage_model.decoder."), ("vae_encoder", "first_stage_model.encoder.")):
+                        sub = model_io.preadjusted_checkpoint_to_params(sd, pref)
+                        if sub:
+                            out[part] = sub
+            elif isinstance(self, FluxPipeline):
                 params = model_io.flux_checkpoint_to_params(sd, self.config.hidden_size, self.config.mlp_ratio)
             else:
                 params = model_io.sd3_checkpoint_to_params(sd)
@@ -530,8 +546,6 @@ class FluxPipeline(DiffusionPipeline):
         vae_encoder_params=None,
         load_encoder: bool = False,
     ):
-        if quantize_mmdit:
-            raise NotImplementedError("4-bit MMDiT variants are SURVEY.md §8 row f4")
         self.float16_dtype = torch.bfloat16                                 # :610
         self._vae_encoder_params, self._load_encoder = vae_encoder_params, load_encoder
         self._setup(w16, a16, shift, model_version, low_memory_mode, local_ckpt, device, params, vae_params,

@@ -150,6 +150,12 @@ int dk_sampler_step(dk_ctx* ctx, int dtype, float* x, const void* xin, const voi
                     float sigma_next, float cfg_weight, void* stream);
 /* y = x * a + b (fp32): latent_format.process_out (__init__.py:732-733) and noise scaling (sampler.py:41-42) */
 int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, float a, float b, void* stream);
+/* MLX affine 4-bit Linear weights -> dense 16-bit (the `*-4bit-quantized` model versions, reference
+ * mlx/model_io.py:728-734, 772-775: nn.quantize with MLX defaults group_size 64, bits 4).
+ * wq [N, K/8] uint32 (8 nibbles per word, element 0 in the low bits); scales, biases [N, K/group_size] 16-bit;
+ * out[n, k] = scales[n, k/group] * q[n, k] + biases[n, k/group]  (one fp32 FMA, rounded once to `dtype`) */
+int dk_dequant_q4(dk_ctx* ctx, int dtype, const uint32_t* wq, const void* scales, const void* biases, void* out,
+                  long long N, int K, int group_size, void* stream);
 /* read_image (__init__.py:536-551): uint8 [pixels, src_channels >= 3] -> 16-bit [pixels, cpad]; channels 0..2 =
  * u8 / 255 * 2 - 1, the padding channels are zero */
 int dk_image_pre(dk_ctx* ctx, int dtype, const uint8_t* img, void* out, long long pixels, int src_channels, int cpad,

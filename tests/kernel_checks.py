@@ -232,6 +232,26 @@ def check_img2img_kernels():
     return out
 
 
+def check_dequant_q4():
+    """dk_dequant_q4 vs the numpy restatement of MLX's dequantisation rule: bit-exact in both 16-bit types"""
+    import numpy as np
+
+    from oracle import quant_ref as qr
+
+    _setup()
+    out = {}
+    rng = np.random.RandomState(3)
+    for (N, K, dt) in [(64, 256, torch.bfloat16), (200, 3072, torch.bfloat16), (72, 128, torch.float16)]:
+        w = (rng.randn(N, K) / math.sqrt(K)).astype(np.float32)
+        wq, sc, bi = qr.quantize_q4(w)
+        sc16, bi16 = torch.from_numpy(sc).to(dt), torch.from_numpy(bi).to(dt)
+        want = torch.from_numpy(qr.dequantize_q4(wq, sc16.float().numpy(), bi16.float().numpy())).to(dt)
+        got = ops.dequant_q4(torch.from_numpy(wq.view(np.int32)).to(DEV), sc16.to(DEV), bi16.to(DEV))
+        assert got.dtype == dt and torch.equal(got.cpu(), want), f"dequant_q4 {N}x{K} {dt}"
+        out[f"{N}x{K}"] = rel_l2(got, torch.from_numpy(w))       # quantisation error itself, for the record
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attention_case(B, S, heads, d, dtype, split=None, name=""):
     h = heads * d
@@ -584,7 +604,7 @@ def check_error_paths():
 ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
     check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
-    check_gemm_pair_kernel, check_conv3x3, check_conv3x3_s2, check_img2img_kernels,
+    check_gemm_pair_kernel, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
     check_attention_v1_kernel, check_attention_v2_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,

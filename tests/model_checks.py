@@ -14,7 +14,8 @@ import torch
 
 import diffusionkit_b200 as dk
 from diffusionkit_b200 import ops
-from diffusionkit_b200.config import VAEDecoderConfig, VAEEncoderConfig, tiny_flux_config, tiny_sd3_config
+from diffusionkit_b200.config import (VAEDecoderConfig, VAEEncoderConfig, tiny_flux_config, tiny_sd3_config,
+                                      tiny_sd35_config)
 from diffusionkit_b200.weights import (init_params, mmdit_param_specs, vae_decoder_param_specs,
                                        vae_encoder_param_specs)
 from oracle import sampler_ref as sr
@@ -82,6 +83,11 @@ def check_mmdit_flux_ragged():
 
 def check_mmdit_sd3_d64_long():
     return _mmdit_case(tiny_sd3_config(hidden=192, heads=3, depth_mm=3), torch.float16, 2, (32, 40), 154)
+
+
+def check_mmdit_sd35_tiny():
+    """SD3.5 shape of the block: learned positional embedding + QK-RMSNorm, fp16 activations, bf16 sinusoid"""
+    return _mmdit_case(tiny_sd35_config(), torch.float16, 2, (8, 12), 24)
 
 
 def _vae_case(dtype, B, lat, tol_psnr):
@@ -318,6 +324,75 @@ def check_pipeline_local_ckpt():
     return {}
 
 
+def check_pipeline_q4_ckpt():
+    """`*-4bit-quantized` model versions: a checkpoint in the reference's saved layout (final names, MLX 4-bit triples
+    for every Linear) loads to exactly the latents of the same weights dequantised by the oracle."""
+    import tempfile
+
+    from safetensors.torch import save_file
+
+    from oracle import quant_ref as qr
+
+    out = {}
+    for kind in ("flux", "sd35"):
+        if kind == "flux":
+            cfg, dtype, Pipe = tiny_flux_config(), torch.bfloat16, dk.FluxPipeline
+            mv, prefix = "argmaxinc/mlx-FLUX.1-schnell-4bit-quantized", ""
+        else:
+            cfg, dtype, Pipe = tiny_sd35_config(), torch.float16, dk.DiffusionPipeline
+            mv, prefix = "argmaxinc/mlx-stable-diffusion-3.5-large-4bit-quantized", "model.diffusion_model."
+        p32 = init_params(mmdit_param_specs(cfg), seed=7, dtype=torch.float32)
+        v16 = {k: v.to(dtype) for k, v in init_params(vae_decoder_param_specs(VAEDecoderConfig()), seed=8,
+                                                       dtype=torch.float32).items()}
+        file, dense = {}, {}
+        nq = 0
+        for k, v in p32.items():
+            if k.endswith(".weight") and v.dim() == 2 and "pos_embed" not in k:      # nn.Linear -> QuantizedLinear
+                wq, sc, bi = qr.quantize_q4(v.numpy())
+                sc16, bi16 = torch.from_numpy(sc).to(dtype), torch.from_numpy(bi).to(dtype)
+                file[prefix + k] = torch.from_numpy(wq.view(np.int32)).view(torch.uint32)
+                file[prefix + k[:-7] + ".scales"], file[prefix + k[:-7] + ".biases"] = sc16, bi16
+                dense[k] = torch.from_numpy(qr.dequantize_q4(wq, sc16.float().numpy(), bi16.float().numpy())).to(dtype)
+                nq += 1
+            else:
+                file[prefix + k] = dense[k] = v.to(dtype)
+        if kind == "sd35":                                # single file: the (dense) VAE rides along, already renamed
+            file.update({"first_stage_model.decoder." + k: v for k, v in v16.items()})
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "q4.safetensors")
+            save_file({k: v.contiguous() for k, v in file.items()}, path)
+            a = Pipe(w16=True, a16=True, model_version=mv, mmdit_config=cfg, local_ckpt=path,
+                     vae_params=None if kind == "sd35" else {k: v.to(DEV) for k, v in v16.items()})
+        b = Pipe(w16=True, a16=True, model_version=mv, mmdit_config=cfg, params={k: v.to(DEV) for k, v in dense.items()},
+                 vae_params={k: v.to(DEV) for k, v in v16.items()})
+        cond, pooled = a.synthetic_text_embeddings(text_len=16)
+        cfgw = 0.0 if kind == "flux" else 4.0
+        la, _ = a.denoise_latents(cond, pooled, num_steps=2, cfg_weight=cfgw, latent_size=(8, 8), seed=3)
+        lb, _ = b.denoise_latents(cond, pooled, num_steps=2, cfg_weight=cfgw, latent_size=(8, 8), seed=3)
+        assert torch.equal(la, lb), kind
+        assert torch.equal(a.decode_latents_to_image(la), b.decode_latents_to_image(lb)), kind
+        out[kind + "_quantised_linears"] = nq
+    return out
+
+
+def check_full_size_sd35_properties():
+    """SD3.5-large at its real width/depth (SD3_8b: 38 blocks, 38 heads x 64, hidden 2432, QK-norm; 8 B synthetic
+    parameters), 512x512, CFG: determinism, batch independence, finiteness."""
+    pipe = dk.DiffusionPipeline(w16=True, a16=True, shift=3.0, model_version="argmaxinc/mlx-stable-diffusion-3.5-large",
+                                load_decoder=False)
+    assert pipe.config.hidden_size == 2432 and pipe.config.head_dim == 64 and pipe.config.use_qk_norm
+    cond, pooled = pipe.synthetic_text_embeddings(n_images=2, text_len=154)
+    kw = dict(num_steps=3, cfg_weight=4.5, latent_size=(64, 64))
+    a, _ = pipe.denoise_latents(cond, pooled, seed=[5, 6], **kw)
+    b, _ = pipe.denoise_latents(cond, pooled, seed=[5, 6], **kw)
+    assert torch.equal(a, b), "denoise loop is not deterministic"
+    assert bool(torch.isfinite(a).all())
+    solo, _ = pipe.denoise_latents(cond[[1, 3]], pooled[[1, 3]], seed=6, **kw)
+    r = rel_l2(a[1:2], solo)
+    assert r <= 1e-5, f"batch composition changed image 1: rel_l2 {r:.3e}"
+    return {"batch_vs_solo_rel_l2": r, "latent_abs_mean": float(a.abs().mean()), "latent_abs_max": float(a.abs().max())}
+
+
 def check_full_size_flux_properties():
     """FLUX.1-schnell at its real width/depth (11.9 B synthetic parameters), 512x512, 4 steps: size-independent
     properties the oracle cannot check in seconds — determinism (no atomics on the path), batch independence
@@ -360,7 +435,8 @@ def check_full_size_vae_properties():
     return {"u8_max_diff_batch_vs_solo": int(d.max()), "mean": float(f2.mean())}
 
 
-ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
+ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_sd35_tiny, check_pipeline_q4_ckpt,
+              check_full_size_sd35_properties, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
               check_vae_decode_tiny, check_vae_decode_batch_fp16, check_vae_encode_tiny, check_vae_encode_batch_fp16,
               check_pipeline_img2img, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
               check_pipeline_errors, check_pipeline_local_ckpt, check_full_size_flux_properties, check_full_size_vae_properties]

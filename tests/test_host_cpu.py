@@ -57,8 +57,11 @@ def test_pipeline_argument_errors():
         DiffusionPipeline(w16=True, a16=True, model_version="no/such-model")
     with pytest.raises(NotImplementedError):
         DiffusionPipeline(w16=False, a16=False)          # fp32 path not provided
-    with pytest.raises(NotImplementedError):
-        FluxPipeline(w16=True, a16=True, quantize_mmdit=True)
+    from diffusionkit_b200._lib import DkError
+
+    with pytest.raises(DkError):                         # valid arguments, but no CUDA device here: refuses loudly
+        FluxPipeline(w16=True, a16=True, quantize_mmdit=True,
+                     model_version="argmaxinc/mlx-FLUX.1-schnell-4bit-quantized")
 
 
 def test_presets_match_reference_values():
@@ -71,6 +74,12 @@ def test_presets_match_reference_values():
     assert f.rope_axes_dim == (16, 56, 56) and f.pooled_text_embed_dim == 768 and f.use_qk_norm
     assert f.patchify_via_reshape and f.pos_embed_type == PositionalEncoding.PreSDPARope and f.dtype == torch.bfloat16
     assert MODEL_CONFIGS["argmaxinc/mlx-FLUX.1-dev"] is FLUX_SCHNELL      # quirk Q1
+    from diffusionkit_b200.config import SD3_8b
+
+    assert (SD3_8b.hidden_size, SD3_8b.num_heads, SD3_8b.head_dim, SD3_8b.depth_multimodal) == (2432, 38, 64, 38)
+    assert SD3_8b.use_qk_norm and SD3_8b.dtype == torch.bfloat16          # reference mlx/config.py:74-76
+    assert MODEL_CONFIGS["argmaxinc/mlx-stable-diffusion-3.5-large-4bit-quantized"] is SD3_8b
+    assert MODEL_CONFIGS["argmaxinc/mlx-FLUX.1-schnell-4bit-quantized"] is FLUX_SCHNELL
 
 
 def test_parameter_trees():
@@ -196,3 +205,29 @@ def test_gloo_world2_weight_broadcast_and_sharding(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "OK 0 [0, 1, 2]" in outs[0] and "OK 1 [3, 4]" in outs[1]
+
+
+def test_read_image_resize_rule(tmp_path):
+    """read_image (reference mlx/__init__.py:536-551): sizes are cut to multiples of 64 with a LANCZOS resize, RGB(A)
+    uint8 -> [-1, 1] float; host-only logic, no device needed"""
+    import numpy as np
+    from PIL import Image
+
+    from diffusionkit_b200.pipeline import DiffusionPipeline
+
+    rng = np.random.RandomState(0)
+    arr = rng.randint(0, 256, (130, 200, 4), dtype=np.uint8)
+    path = str(tmp_path / "im.png")
+    Image.fromarray(arr).save(path)
+    u8 = DiffusionPipeline._load_image_u8(None, path)
+    assert u8.shape == (128, 192, 4) and u8.dtype == np.uint8
+    same = DiffusionPipeline._load_image_u8(None, arr[:128, :192])
+    assert same.shape == (128, 192, 3) and np.array_equal(same, arr[:128, :192, :3])   # already aligned: untouched
+    f = DiffusionPipeline.read_image(DiffusionPipeline.__new__(DiffusionPipeline), arr[:64, :64])
+    assert tuple(f.shape) == (1, 64, 64, 3) and abs(float(f[0, 0, 0, 0]) - (arr[0, 0, 0] / 255 * 2 - 1)) < 1e-6
+    import pytest
+
+    with pytest.raises(ValueError):
+        DiffusionPipeline._load_image_u8(None, arr[:40, :40])
+    with pytest.raises(ValueError):
+        DiffusionPipeline._load_image_u8(None, arr[:64, :64, 0])

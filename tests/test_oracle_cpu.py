@@ -147,3 +147,27 @@ def test_compute_psnr_definition():
     # utils.py:70-82: 20 log10((peak + 1e-5) / (rmse + 1e-10))
     assert abs(sr.compute_psnr(a, b) - 20 * np.log10((4 + 1e-5) / (0.1 + 1e-10))) < 1e-9
     assert sr.process_out(torch.tensor([0.0]), "flux").item() == np.float32(0.1159)
+
+
+def test_q4_oracle_layout_and_roundtrip():
+    """MLX 4-bit layout: element j of a word sits in bits [4j, 4j+4); dequantised value = scale * q + bias"""
+    import numpy as np
+
+    from oracle import quant_ref as qr
+
+    assert qr.unpack_q4(np.array([[0x76543210]], dtype=np.uint32)).tolist() == [[0, 1, 2, 3, 4, 5, 6, 7]]
+    rng = np.random.RandomState(0)
+    w = rng.randn(16, 256).astype(np.float32)
+    wq, sc, bi = qr.quantize_q4(w)
+    assert wq.shape == (16, 32) and sc.shape == bi.shape == (16, 4) and wq.dtype == np.uint32
+    back = qr.dequantize_q4(wq, sc, bi)
+    step = np.repeat(sc, 64, axis=1)
+    assert np.all(np.abs(back - w) <= 0.5 * step + 1e-6)           # round-to-nearest inside [min, max]
+    # group extremes are represented exactly (q = 0 and q = 15)
+    g = w.reshape(16, 4, 64)
+    assert np.allclose(back.reshape(16, 4, 64).min(-1), g.min(-1), atol=1e-6)
+    assert np.allclose(back.reshape(16, 4, 64).max(-1), g.max(-1), atol=1e-5)
+    # KAT: scales 0.5, bias -1, nibbles 0..7 -> -1, -0.5, ..., 2.5
+    kat = qr.dequantize_q4(np.array([[0x76543210]], dtype=np.uint32), np.array([[0.5]], np.float32),
+                           np.array([[-1.0]], np.float32), group_size=8)
+    assert kat.tolist() == [[-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0, 2.5]]
