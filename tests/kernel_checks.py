@@ -215,9 +215,11 @@ def check_img2img_kernels():
         for cs in (3, 4):
             img = torch.randint(0, 256, (2, 8, 12, cs), dtype=torch.uint8, device=DEV)
             got = ops.image_pre(img, dt, 64)
-            ref = torch.zeros((2, 8, 12, 64), dtype=torch.float32, device=DEV)
-            ref[..., :3] = img[..., :3].float() / 255 * 2 - 1.0
-            assert torch.equal(got, ref.to(dt)), f"image_pre {dt} {cs}"
+            # reference arithmetic on the CPU: torch's CUDA div-by-scalar multiplies by the reciprocal, the reference
+            # (and dk_image_pre) divide
+            ref = torch.zeros((2, 8, 12, 64), dtype=torch.float32)
+            ref[..., :3] = img.cpu()[..., :3].float() / 255 * 2 - 1.0
+            assert torch.equal(got.cpu(), ref.to(dt)), f"image_pre {dt} {cs}"
     hidden = _rand((1, 8, 8, 32), torch.bfloat16, 2.0)
     hidden[0, 0, 0, 16] = 50.0       # logvar clipped at 20
     hidden[0, 0, 1, 16] = -80.0      # ... and at -30
@@ -248,7 +250,7 @@ def check_dequant_q4():
         want = torch.from_numpy(qr.dequantize_q4(wq, sc16.float().numpy(), bi16.float().numpy())).to(dt)
         got = ops.dequant_q4(torch.from_numpy(wq.view(np.int32)).to(DEV), sc16.to(DEV), bi16.to(DEV))
         assert got.dtype == dt and torch.equal(got.cpu(), want), f"dequant_q4 {N}x{K} {dt}"
-        out[f"{N}x{K}"] = rel_l2(got, torch.from_numpy(w))       # quantisation error itself, for the record
+        out[f"{N}x{K}"] = rel_l2(got.cpu(), torch.from_numpy(w))       # quantisation error itself, for the record
     return out
 
 
