@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libdkb200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "dkb200.h")
 
 DK_BF16, DK_FP16 = 0, 1
-ACT_NONE, ACT_GELU_ERF, ACT_SILU = 0, 1, 2
+ACT_NONE, ACT_GELU_ERF, ACT_SILU, ACT_QUICK_GELU = 0, 1, 2, 3
 
 vp = C.c_void_p
 i32 = C.c_int
@@ -62,6 +62,12 @@ SIGNATURES = {
     "dk_sampler_prepare": (i32, [vp, i32, vp, vp, i64, i32, vp]),
     "dk_sampler_step": (i32, [vp, i32, vp, vp, vp, i64, f32, f32, f32, vp]),
     "dk_axpb_f32": (i32, [vp, vp, vp, i64, f32, f32, vp]),
+    "dk_embedding": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "dk_layernorm": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, f32, vp]),
+    "dk_rmsnorm_f32": (i32, [vp, i32, vp, vp, vp, i32, i32, f32, vp]),
+    "dk_add_f32_16": (i32, [vp, i32, vp, vp, i64, vp]),
+    "dk_glu_gelu": (i32, [vp, i32, vp, vp, i64, i32, vp]),
+    "dk_attention_small": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
     "dk_dequant_q4": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, vp]),
     "dk_image_pre": (i32, [vp, i32, vp, vp, i64, i32, i32, vp]),
     "dk_axpby_f32": (i32, [vp, vp, vp, vp, i64, f32, f32, vp]),

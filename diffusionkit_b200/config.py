@@ -140,3 +140,47 @@ def tiny_sd3_config(hidden: int = 128, heads: int = 2, depth_mm: int = 3) -> MMD
     assert hidden // heads == 64
     return replace(SD3_2b, num_heads=heads, depth_multimodal=depth_mm, hidden_size_override=hidden,
                    max_latent_resolution=24, pooled_text_embed_dim=64, token_level_text_embed_dim=128)
+
+
+@dataclass
+class CLIPTextModelConfig:
+    """reference mlx/config.py:144-152 (defaults are the reference's; CLIP_L / CLIP_G below are the values of the
+    config.json files the reference downloads, model_io.py:799-816)"""
+
+    num_layers: int = 23
+    model_dims: int = 1024
+    num_heads: int = 16
+    max_length: int = 77
+    vocab_size: int = 49408
+    projection_dim: Optional[int] = None
+    hidden_act: str = "quick_gelu"
+
+
+CLIP_L = CLIPTextModelConfig(num_layers=12, model_dims=768, num_heads=12, projection_dim=None, hidden_act="quick_gelu")
+CLIP_G = CLIPTextModelConfig(num_layers=32, model_dims=1280, num_heads=20, projection_dim=1280, hidden_act="gelu")
+
+
+@dataclass
+class T5EncoderConfig:
+    """The fields of transformers.T5Config the reference reads (mlx/t5.py), with google/t5-v1_1-xxl's values
+    (reference model_io.py:928, T5Config.from_pretrained("google/t5-v1_1-xxl"))."""
+
+    vocab_size: int = 32128
+    d_model: int = 4096
+    d_kv: int = 64
+    d_ff: int = 10240
+    num_layers: int = 24
+    num_heads: int = 64
+    relative_attention_num_buckets: int = 32
+    relative_attention_max_distance: int = 128
+    layer_norm_epsilon: float = 1e-6
+    feed_forward_proj: str = "gated-gelu"
+
+
+def tiny_clip_config(projection: bool = True, act: str = "quick_gelu") -> CLIPTextModelConfig:
+    return CLIPTextModelConfig(num_layers=3, model_dims=128, num_heads=2, max_length=77, vocab_size=1000,
+                               projection_dim=64 if projection else None, hidden_act=act)
+
+
+def tiny_t5_config() -> T5EncoderConfig:
+    return T5EncoderConfig(vocab_size=512, d_model=256, d_kv=64, d_ff=512, num_layers=3, num_heads=4)

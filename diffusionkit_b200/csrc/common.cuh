@@ -447,6 +447,13 @@ __device__ __forceinline__ float silu_f(float v) {
   return __fdividef(v, 1.0f + e);
 }
 
+// x * sigmoid(1.702 x): mlx nn.gelu_fast_approx, CLIP's "quick_gelu" (reference mlx/clip.py:11)
+__device__ __forceinline__ float quick_gelu_f(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.702f * 1.4426950408889634f * v));
+  return __fdividef(v, 1.0f + e);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -213,7 +213,7 @@ __global__ void act_kernel(const T* __restrict__ x, T* __restrict__ y, long long
     float a[8];
     load8(x + i * 8, a);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = act == DK_ACT_SILU ? silu_f(a[j]) : (act == DK_ACT_GELU_ERF ? gelu_erf(a[j]) : a[j]);
+    for (int j = 0; j < 8; ++j) a[j] = act == DK_ACT_SILU ? silu_f(a[j]) : (act == DK_ACT_GELU_ERF ? gelu_erf(a[j]) : (act == DK_ACT_QUICK_GELU ? quick_gelu_f(a[j]) : a[j]));
     store8(y + i * 8, a);
   }
 }

@@ -209,6 +209,9 @@ for (int chunk = 0; chunk < NCH; ++chunk) {
         } else if (e.act == DK_ACT_SILU) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+        } else if (e.act == DK_ACT_QUICK_GELU) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = quick_gelu_f(v[i]);
         }
         if (gate != nullptr) {
           const uint4 g4 = *reinterpret_cast<const uint4*>(gate + static_cast<long long>(batch) * e.gate_ld + n);

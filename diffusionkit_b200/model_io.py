@@ -232,6 +232,59 @@ def vae_encoder_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "encod
     return _vae_checkpoint_to_params(sd, prefix, "down")
 
 
+# ------------------------------------------------------------------------------------------------ text encoders
+def clip_checkpoint_to_params(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """HF CLIPTextModel(WithProjection) safetensors -> CLIPTextModel parameter tree
+    (reference map_clip_text_encoder_weights, model_io.py:611-636)."""
+    out: Dict[str, Tensor] = {}
+    for key, v in sd.items():
+        k = key
+        for pre in ("text_model.", "embeddings.", "encoder."):
+            if k.startswith(pre):
+                k = k[len(pre):]
+        if k == "position_ids":
+            continue                                      # a buffer older checkpoints carry; not a parameter
+        k = k.replace("self_attn.", "attention.")
+        k = k.replace("q_proj.", "query_proj.").replace("k_proj.", "key_proj.").replace("v_proj.", "value_proj.")
+        k = k.replace("mlp.fc1", "linear1").replace("mlp.fc2", "linear2")
+        out[k] = v
+    return out
+
+
+def t5_checkpoint_to_params(sd: Dict[str, Tensor], prefix: str = "") -> Dict[str, Tensor]:
+    """HF T5EncoderModel (t5xxl.safetensors) -> SD3T5Encoder parameter tree
+    (reference t5_encoder_state_dict_adjustments, model_io.py:565-608)."""
+    out: Dict[str, Tensor] = {}
+    attn = {"q": "query_proj", "k": "key_proj", "v": "value_proj", "o": "out_proj"}
+    for key, v in sd.items():
+        k = key[len(prefix):] if prefix and key.startswith(prefix) else key
+        if k in ("shared.weight",):
+            continue                                      # same tensor as encoder.embed_tokens.weight (:601-603)
+        if k == "encoder.embed_tokens.weight":
+            out["wte.weight"] = v
+        elif k == "encoder.final_layer_norm.weight":
+            out["encoder.ln.weight"] = v
+        elif k == "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight":
+            out["encoder.relative_attention_bias.embeddings.weight"] = v
+        else:
+            m = re.fullmatch(r"encoder\.block\.(\d+)\.layer\.(0|1)\.(.+)", k)
+            if not m:
+                raise KeyError(f"unrecognised T5 key {key}")
+            i, sub, rest = m.groups()
+            base = f"encoder.layers.{i}."
+            if rest == "layer_norm.weight":
+                out[base + f"ln{int(sub) + 1}.weight"] = v
+            elif rest.startswith("SelfAttention."):
+                out[base + f"attention.{attn[rest.split('.')[1]]}.weight"] = v
+            elif rest.startswith("DenseReluDense."):
+                out[base + "dense." + rest[len("DenseReluDense."):]] = v
+            else:
+                raise KeyError(f"unrecognised T5 key {key}")
+    if "wte.weight" not in out and "shared.weight" in sd:
+        out["wte.weight"] = sd["shared.weight"]
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ 4-bit variants
 def is_q4_checkpoint(sd: Dict[str, Tensor]) -> bool:
     return any(k.endswith(".scales") for k in sd)

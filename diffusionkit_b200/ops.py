@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_SILU, Context, GemmArgs, dtype_code, ptr
+from ._lib import ACT_GELU_ERF, ACT_NONE, ACT_QUICK_GELU, ACT_SILU, Context, GemmArgs, dtype_code, ptr
 
 _ctx = {}
 
@@ -231,6 +231,75 @@ def axpb(x, a: float, b: float, out=None):
         out = torch.empty_like(x)
     c = ctx(x.device.index)
     c.call("dk_axpb_f32", ptr(x), ptr(out), x.numel(), a, b)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ text encoders
+def embedding(table, ids, pos=None, out=None):
+    """out[i] = table[ids[i]] (+ pos[i % len(pos)]); ids int32 (any shape, flattened)"""
+    _chk16(table, "embedding.table")
+    assert table.is_contiguous() and ids.dtype == torch.int32 and ids.is_contiguous() and ids.is_cuda
+    n, d = ids.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((n, d), dtype=table.dtype, device=table.device)
+    c = ctx(table.device.index)
+    c.call("dk_embedding", dtype_code(table.dtype), ptr(table), ptr(ids), ptr(pos), ptr(out), n, d, table.shape[0],
+           0 if pos is None else pos.shape[0])
+    return out
+
+
+def layernorm(x, weight, bias, eps: float = 1e-5, out=None):
+    _chk16(x, "layernorm.x")
+    rows, h = x.shape
+    assert x.is_contiguous() and weight.is_contiguous() and bias.is_contiguous()
+    if out is None:
+        out = torch.empty_like(x)
+    c = ctx(x.device.index)
+    c.call("dk_layernorm", dtype_code(x.dtype), ptr(x), ptr(out), ptr(weight), ptr(bias), rows, h, eps)
+    return out
+
+
+def rmsnorm_f32(x, weight, eps: float = 1e-6, out=None):
+    """x fp32 [rows, d] -> 16-bit (weight's dtype) weight * x * rsqrt(mean(x^2) + eps)"""
+    _chk16(weight, "rmsnorm_f32.weight")
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 2
+    if out is None:
+        out = torch.empty(x.shape, dtype=weight.dtype, device=x.device)
+    c = ctx(x.device.index)
+    c.call("dk_rmsnorm_f32", dtype_code(weight.dtype), ptr(x), ptr(weight), ptr(out), x.shape[0], x.shape[1], eps)
+    return out
+
+
+def add_f32_16(x, y):
+    _chk16(y, "add_f32_16.y")
+    assert x.dtype == torch.float32 and x.is_contiguous() and y.is_contiguous() and x.numel() == y.numel()
+    c = ctx(x.device.index)
+    c.call("dk_add_f32_16", dtype_code(y.dtype), ptr(x), ptr(y), x.numel())
+    return x
+
+
+def glu_gelu(h, out=None):
+    _chk16(h, "glu_gelu.h")
+    rows, F2 = h.shape
+    assert h.is_contiguous() and F2 % 2 == 0
+    if out is None:
+        out = torch.empty((rows, F2 // 2), dtype=h.dtype, device=h.device)
+    c = ctx(h.device.index)
+    c.call("dk_glu_gelu", dtype_code(h.dtype), ptr(h), ptr(out), rows, F2 // 2)
+    return out
+
+
+def attention_small(qkv, B: int, S: int, heads: int, scale: float, rel_bias=None, causal: bool = False, out=None):
+    """packed (q | k | v) [B*S, 3*heads*64] -> [B*S, heads*64]; rel_bias [heads, 2S-1] or None"""
+    _chk16(qkv, "attention_small.qkv")
+    assert qkv.is_contiguous() and tuple(qkv.shape) == (B * S, 3 * heads * 64)
+    if rel_bias is not None:
+        assert rel_bias.dtype == qkv.dtype and rel_bias.is_contiguous() and tuple(rel_bias.shape) == (heads, 2 * S - 1)
+    if out is None:
+        out = torch.empty((B * S, heads * 64), dtype=qkv.dtype, device=qkv.device)
+    c = ctx(qkv.device.index)
+    c.call("dk_attention_small", dtype_code(qkv.dtype), ptr(qkv), ptr(rel_bias), ptr(out), B, S, heads, 64, scale,
+           1 if causal else 0)
     return out
 
 

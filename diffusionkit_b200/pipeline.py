@@ -263,12 +263,72 @@ class DiffusionPipeline:
         self.encoder = VAEEncoder(ep, VAEEncoderConfig(), device=self.device)
         self._vae_encoder_params = None
 
-    # ------------------------------------------------------------------ text (row f2: not on the hot path)
+    # ------------------------------------------------------------------ text
+    def load_text_encoders(self, clip_l=None, clip_g=None, t5=None, *, tokenizer_l=None, tokenizer_g=None,
+                           t5_tokenizer=None, clip_l_config=None, clip_g_config=None, t5_config=None):
+        """Build CLIP-L (+ CLIP-G for SD3) and the T5 encoder on the device, and attach their tokenizers.
+        clip_l / clip_g / t5: parameter dicts with the reference's names (model_io.clip_checkpoint_to_params /
+        t5_checkpoint_to_params convert upstream safetensors), or None for the deterministic synthetic initialiser.
+        tokenizer_*: tokenizer.Tokenizer / tokenizer.T5Tokenizer objects built from local vocabulary files (the
+        reference downloads all of this in check_and_load_models, :118-143; no network here)."""
+        from .config import CLIP_G, CLIP_L, T5EncoderConfig
+        from .text_encoders import CLIPTextModel, SD3T5Encoder, clip_param_specs, t5_param_specs
+
+        def build(cls, params, cfg, specs, seed, dtype=None):
+            dtype = dtype or self.dtype
+            if params is None:
+                params = init_params(specs(cfg), seed=self._weight_seed + seed, dtype=dtype, device=self.device)
+            return cls({k: v.to(device=self.device, dtype=dtype) for k, v in params.items()}, cfg, device=self.device)
+
+        self.clip_l = build(CLIPTextModel, clip_l, clip_l_config or CLIP_L, clip_param_specs, 3)
+        if self.use_clip_g:
+            self.clip_g = build(CLIPTextModel, clip_g, clip_g_config or CLIP_G, clip_param_specs, 4)
+        if self.use_t5:
+            # T5-XXL's feed-forward overflows fp16 — the reference runs it in fp32 for that reason (t5.py:214-224).
+            # Here its GEMMs take 16-bit inputs, so the T5 stack always computes in bf16 (fp32's range), also
+            # inside the fp16 SD3 pipeline; the output is cast to the activation dtype.
+            self.t5_encoder = build(SD3T5Encoder, t5, t5_config or T5EncoderConfig(), t5_param_specs, 5,
+                                    dtype=torch.bfloat16)
+        self.tokenizer_l, self.tokenizer_g, self.t5_tokenizer = tokenizer_l, tokenizer_g, t5_tokenizer
+
+    def _need_text_stack(self, *names):
+        missing = [n for n in names if getattr(self, n, None) is None]
+        if missing:
+            raise DkError(
+                f"encode_text needs {', '.join(missing)}: call load_text_encoders(...) with local weights and "
+                "tokenizer files first (nothing can be downloaded here), or pass `conditioning` / `pooled_conditioning`")
+
+    def _tokenize(self, tokenizer, text: str, negative_text: Optional[str] = None):
+        """reference :174-195 — note that a None negative prompt becomes "" first, so two rows always come back (Q11)"""
+        if negative_text is None:
+            negative_text = ""
+        pad_token = tokenizer.eos_token if tokenizer.pad_with_eos else 0
+        tokens = [list(tokenizer.tokenize(text))]
+        if tokenizer.pad_to_max_length:
+            tokens[0].extend([pad_token] * (tokenizer.max_length - len(tokens[0])))
+        tokens += [list(tokenizer.tokenize(negative_text))]
+        N = max(len(t) for t in tokens)
+        tokens = [t + [pad_token] * (N - len(t)) for t in tokens]
+        return torch.tensor(tokens, dtype=torch.int64)
+
     def encode_text(self, text: str, cfg_weight: float = 7.5, negative_text: str = ""):
-        raise NotImplementedError(
-            "text encoders (CLIP-L/G, T5-XXL; reference mlx/clip.py, mlx/t5.py) are outside the denoise+decode hot "
-            "path (SURVEY.md §8 row f2): pass `conditioning` / `pooled_conditioning`, or use "
-            "synthetic_text_embeddings()")
+        """reference :197-251 -> (conditioning (2, 77 + T5, 4096), pooled (2, 2048)) in the activation dtype"""
+        need = ["clip_l", "tokenizer_l", "clip_g", "tokenizer_g"] + (["t5_encoder", "t5_tokenizer"] if self.use_t5 else [])
+        self._need_text_stack(*need)
+        neg = negative_text if cfg_weight > 1 else None
+        cl = self.clip_l(self._tokenize(self.tokenizer_l, text, neg))
+        cg = self.clip_g(self._tokenize(self.tokenizer_g, text, neg))
+        conditioning = torch.cat([cl.hidden_states[-2], cg.hidden_states[-2]], dim=-1)
+        pooled_conditioning = torch.cat([cl.pooled_output, cg.pooled_output], dim=-1)
+        pad = torch.zeros((conditioning.shape[0], conditioning.shape[1], 4096 - conditioning.shape[2]),
+                          dtype=conditioning.dtype, device=self.device)
+        conditioning = torch.cat([conditioning, pad], dim=-1)
+        if self.use_t5:
+            t5_conditioning = self.t5_encoder(self._tokenize(self.t5_tokenizer, text, neg)).to(conditioning.dtype)
+        else:
+            t5_conditioning = torch.zeros_like(conditioning)
+        conditioning = torch.cat([conditioning, t5_conditioning], dim=1)
+        return conditioning, pooled_conditioning
 
     def text_shapes(self, cfg_weight: float) -> Tuple[Tuple[int, int], Tuple[int, int]]:
         """(conditioning (Bc, T, 4096), pooled (Bc, P)) shapes the reference produces for ONE image."""
@@ -555,3 +615,16 @@ class FluxPipeline(DiffusionPipeline):
         self.use_t5 = True
         self.use_clip_g = False
         self.quantize_mmdit = quantize_mmdit
+
+    def encode_text(self, text: str, cfg_weight: float = 7.5, negative_text: str = ""):
+        """reference :642-671: CLIP-L pooled output + T5 sequence of the POSITIVE prompt only, T5 padded with zeros to
+        T5_MAX_LENGTH -> (conditioning (1, T5, 4096), pooled (1, 768))"""
+        self._need_text_stack("clip_l", "tokenizer_l", "t5_encoder", "t5_tokenizer")
+        neg = negative_text if cfg_weight > 1 else None
+        tokens_l = self._tokenize(self.tokenizer_l, text, neg)
+        pooled_conditioning = self.clip_l(tokens_l[[0], :]).pooled_output
+        tokens_t5 = self._tokenize(self.t5_tokenizer, text, neg)
+        padded = torch.zeros((1, T5_MAX_LENGTH[self.model_version]), dtype=tokens_t5.dtype)
+        padded[:, : tokens_t5.shape[1]] = tokens_t5[[0], :]
+        conditioning = self.t5_encoder(padded).to(self.activation_dtype)
+        return conditioning, pooled_conditioning

@@ -34,6 +34,7 @@ extern "C" {
 #define DK_ACT_NONE 0
 #define DK_ACT_GELU_ERF 1 /* mlx nn.GELU() exact erf — mmdit.py:421,835 */
 #define DK_ACT_SILU 2
+#define DK_ACT_QUICK_GELU 3 /* x * sigmoid(1.702 x): mlx nn.gelu_fast_approx, CLIP-L "quick_gelu" — clip.py:11 */
 
 typedef struct dk_ctx dk_ctx;
 
@@ -150,6 +151,25 @@ int dk_sampler_step(dk_ctx* ctx, int dtype, float* x, const void* xin, const voi
                     float sigma_next, float cfg_weight, void* stream);
 /* y = x * a + b (fp32): latent_format.process_out (__init__.py:732-733) and noise scaling (sampler.py:41-42) */
 int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, float a, float b, void* stream);
+/* ---- text encoders: CLIP-L/G (mlx/clip.py) and the T5-XXL encoder (mlx/t5.py) ------------- */
+/* out[i] = table[ids[i]] (+ pos[i % pos_len]); table [vocab, d], pos [pos_len, d] or NULL   (clip.py:97-98, t5.py:322) */
+int dk_embedding(dk_ctx* ctx, int dtype, const void* table, const int* ids, const void* pos, void* out, long long n,
+                 int d, int vocab, int pos_len, void* stream);
+/* y = LN(x) * weight + bias, biased variance, fp32 statistics (mlx nn.LayerNorm; clip.py:32-33,78) */
+int dk_layernorm(dk_ctx* ctx, int dtype, const void* x, void* y, const void* weight, const void* bias, int rows, int h,
+                 float eps, void* stream);
+/* T5 RMSNorm over the fp32 residual stream: y = (dtype)(weight * x * rsqrt(mean(x^2) + eps))   (t5.py:150-170) */
+int dk_rmsnorm_f32(dk_ctx* ctx, int dtype, const float* x, const void* weight, void* y, int rows, int d, float eps,
+                   void* stream);
+/* x (fp32) += y (16-bit): T5 keeps the residual stream in fp32 (t5.py:214-221) */
+int dk_add_f32_16(dk_ctx* ctx, int dtype, float* x, const void* y, long long n, void* stream);
+/* out[r, f] = gelu_erf(h[r, f]) * h[r, F + f], h [rows, 2F] = x @ [wi_0 | wi_1]^T   (t5.py:195-199) */
+int dk_glu_gelu(dk_ctx* ctx, int dtype, const void* h, void* out, long long rows, int F, void* stream);
+/* short-sequence attention (S <= 512, head dim 64) over a packed (q | k | v) projection [B*S, 3*heads*64]:
+ * out = softmax(scale * q k^T + rel_bias[head][j - i + S - 1] + (causal ? -6e4 * [j > i] : 0)) v
+ * rel_bias [heads, 2S-1] 16-bit or NULL (T5 relative-position bias, t5.py:21-102); causal: CLIP mask (clip.py:84-90) */
+int dk_attention_small(dk_ctx* ctx, int dtype, const void* qkv, const void* rel_bias, void* out, int B, int S, int heads,
+                       int head_dim, float scale, int causal, void* stream);
 /* MLX affine 4-bit Linear weights -> dense 16-bit (the `*-4bit-quantized` model versions, reference
  * mlx/model_io.py:728-734, 772-775: nn.quantize with MLX defaults group_size 64, bits 4).
  * wq [N, K/8] uint32 (8 nibbles per word, element 0 in the low bits); scales, biases [N, K/group_size] 16-bit;

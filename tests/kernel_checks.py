@@ -254,6 +254,76 @@ def check_dequant_q4():
     return out
 
 
+def check_text_kernels():
+    """csrc/text.cu: embedding, LayerNorm(affine), T5 RMSNorm over fp32, fp32 += 16-bit, gated GELU, quick-GELU epilogue"""
+    from diffusionkit_b200._lib import ACT_QUICK_GELU
+
+    _setup()
+    out = {}
+    for dt in (torch.bfloat16, torch.float16):
+        table, pos = _rand((50, 128), dt), _rand((7, 128), dt)
+        ids = torch.randint(0, 50, (3, 7), dtype=torch.int32, device=DEV)
+        got = ops.embedding(table, ids.reshape(-1).contiguous(), pos=pos)
+        want = (table.float()[ids.long()] + pos.float()[None]).to(dt).reshape(21, 128)
+        assert torch.equal(got, want), f"embedding+pos {dt}"
+        assert torch.equal(ops.embedding(table, ids.reshape(-1).contiguous()), table[ids.long().reshape(-1)])
+    for (rows, h, dt) in [(77, 768, torch.bfloat16), (154, 1280, torch.float16), (5, 128, torch.bfloat16)]:
+        x, w, b = _rand((rows, h), dt, 2.0), _rand((h,), dt, 0.5) + 1.0, _rand((h,), dt, 0.3)
+        ref = torch.nn.functional.layer_norm(x.float(), (h,), w.float(), b.float(), 1e-5)
+        out[f"ln_{h}"] = _assert_close(f"layernorm_{h}", ops.layernorm(x, w, b, 1e-5), ref, 4e-3)
+    for (rows, d, dt) in [(64, 4096, torch.bfloat16), (9, 256, torch.bfloat16), (3, 1000, torch.float16)]:
+        x = torch.randn((rows, d), device=DEV) * 30.0
+        w = _rand((d,), dt, 0.2) + 1.0
+        ref = w.float() * x * torch.rsqrt(x.square().mean(-1, keepdim=True) + 1e-6)
+        out[f"rms_{d}"] = _assert_close(f"rmsnorm_f32_{d}", ops.rmsnorm_f32(x, w, 1e-6), ref, 4e-3)
+    x32, y16 = torch.randn(4096, device=DEV), _rand((4096,), torch.bfloat16)
+    assert torch.equal(ops.add_f32_16(x32.clone(), y16), x32 + y16.float())
+    hgl = _rand((33, 2 * 512), torch.bfloat16, 2.0)
+    ref = torch.nn.functional.gelu(hgl.float()[:, :512]) * hgl.float()[:, 512:]
+    out["glu"] = _assert_close("glu_gelu", ops.glu_gelu(hgl), ref, 4e-3)
+    a, wq = _rand((77, 256), torch.bfloat16), _rand((512, 256), torch.bfloat16, 1 / 16)
+    bq = _rand((512,), torch.bfloat16, 0.5)
+    z = a.float() @ wq.float().t() + bq.float()
+    out["quick_gelu"] = _assert_close("gemm_quick_gelu", ops.gemm(a, wq, bias=bq, act=ACT_QUICK_GELU),
+                                      z * torch.sigmoid(1.702 * z), 4e-3)
+    return out
+
+
+def _attention_small_case(B, S, heads, dt, causal, rel, scale, name):
+    qkv = _rand((B * S, 3 * heads * 64), dt)
+    q, k, v = [t.reshape(B, S, heads, 64).permute(0, 2, 1, 3).float() for t in qkv.split(heads * 64, dim=1)]
+    s = scale * (q @ k.transpose(-1, -2))
+    rel_bias = None
+    if rel:
+        rel_bias = _rand((heads, 2 * S - 1), dt, 2.0)
+        idx = (torch.arange(S, device=DEV)[None, :] - torch.arange(S, device=DEV)[:, None]) + S - 1     # j - i + S - 1
+        s = s + rel_bias.float()[:, idx][None]
+    if causal:
+        i = torch.arange(S, device=DEV)
+        s = s + (i[:, None] < i[None]).float() * -6e4
+    ref = (torch.softmax(s, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * S, heads * 64)
+    got = ops.attention_small(qkv, B, S, heads, scale, rel_bias=rel_bias, causal=causal)
+    return _assert_close(name, got, ref, 6e-3)
+
+
+def check_attention_small():
+    """short-sequence attention (text encoders): CLIP causal mask, T5 relative bias, ragged and maximum lengths"""
+    _setup()
+    out = {}
+    out["clip_77"] = _attention_small_case(2, 77, 12, torch.bfloat16, True, False, 0.125, "atts_clip77")
+    out["clip_fp16_20h"] = _attention_small_case(1, 77, 20, torch.float16, True, False, 0.125, "atts_clip_fp16")
+    out["t5_256"] = _attention_small_case(1, 256, 8, torch.bfloat16, False, True, 1.0, "atts_t5_256")
+    out["t5_512"] = _attention_small_case(2, 512, 4, torch.bfloat16, False, True, 1.0, "atts_t5_512")
+    out["ragged_33"] = _attention_small_case(1, 33, 2, torch.bfloat16, True, True, 0.5, "atts_33")
+    out["one_token"] = _attention_small_case(1, 1, 1, torch.bfloat16, False, False, 1.0, "atts_1")
+    c = ops.ctx(0)
+    qkv = _rand((513, 192), torch.bfloat16)
+    o = torch.empty((513, 64), dtype=torch.bfloat16, device=DEV)
+    rc = c.lib.dk_attention_small(c.handle, 0, ops.ptr(qkv), None, ops.ptr(o), 1, 513, 1, 64, 1.0, 0, None)
+    assert rc != 0 and b"512" in c.lib.dk_last_error()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ attention
 def _attention_case(B, S, heads, d, dtype, split=None, name=""):
     h = heads * d
@@ -607,6 +677,7 @@ ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
     check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
     check_gemm_pair_kernel, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
+    check_text_kernels, check_attention_small,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
     check_attention_v1_kernel, check_attention_v2_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,

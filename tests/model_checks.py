@@ -8,6 +8,7 @@ Tolerances (stated per SURVEY.md §8c): 16-bit kernels vs the fp32 oracle —
 """
 import math
 import os
+from dataclasses import replace
 
 import numpy as np
 import torch
@@ -375,6 +376,185 @@ def check_pipeline_q4_ckpt():
     return out
 
 
+def _clip_case(cfg, dtype, B, N, tol):
+    from diffusionkit_b200.text_encoders import CLIPTextModel, clip_param_specs
+    from oracle.text_ref import CLIPTextModelRef
+
+    p16 = {k: v.to(dtype) for k, v in init_params(clip_param_specs(cfg), seed=21, dtype=torch.float32).items()}
+    gen = torch.Generator().manual_seed(2)
+    tokens = torch.randint(1, cfg.vocab_size - 1, (B, N), generator=gen)
+    for b in range(B):
+        tokens[b, N - 1 - 3 * b] = cfg.vocab_size - 1                  # EOS (largest id) at different positions
+    pooled, last, hidden = CLIPTextModelRef({k: v.float() for k, v in p16.items()}, cfg.num_layers, cfg.num_heads,
+                                            cfg.hidden_act)(tokens)
+    out = CLIPTextModel({k: v.to(DEV) for k, v in p16.items()}, cfg)(tokens)
+    torch.cuda.synchronize()
+    res = {"last": rel_l2(out.last_hidden_state, last), "pooled": rel_l2(out.pooled_output, pooled),
+           "hidden_m2": rel_l2(out.hidden_states[-2], hidden[-2])}
+    assert len(out.hidden_states) == cfg.num_layers
+    for k, v in res.items():
+        assert v <= tol, f"clip {k} rel_l2 {v:.3e}"
+    return res
+
+
+def check_clip_tiny():
+    from diffusionkit_b200.config import tiny_clip_config
+
+    a = _clip_case(tiny_clip_config(True, "quick_gelu"), torch.bfloat16, 2, 77, 2e-2)
+    b = _clip_case(tiny_clip_config(False, "gelu"), torch.float16, 3, 20, 3e-3)
+    return {"bf16_quick_gelu": a, "fp16_gelu_noproj": b}
+
+
+def check_t5_tiny():
+    from diffusionkit_b200.config import tiny_t5_config
+    from diffusionkit_b200.text_encoders import SD3T5Encoder, t5_param_specs
+    from oracle.text_ref import T5EncoderRef
+
+    cfg = tiny_t5_config()
+    p32 = init_params(t5_param_specs(cfg), seed=22, dtype=torch.float32)
+    p32["encoder.relative_attention_bias.embeddings.weight"] *= 50.0        # make the position bias matter
+    p32["wte.weight"] *= 50.0                                               # O(1) embeddings
+    p16 = {k: v.to(torch.bfloat16) for k, v in p32.items()}
+    gen = torch.Generator().manual_seed(3)
+    out = {}
+    enc = SD3T5Encoder({k: v.to(DEV) for k, v in p16.items()}, cfg)
+    ref = T5EncoderRef({k: v.float() for k, v in p16.items()}, cfg.num_layers, cfg.num_heads)
+    for (B, L) in [(2, 64), (1, 200)]:
+        tokens = torch.randint(0, cfg.vocab_size, (B, L), generator=gen)
+        got = enc(tokens)
+        torch.cuda.synchronize()
+        assert got.shape == (B, L, cfg.d_model)
+        r = rel_l2(got, ref(tokens))
+        assert r <= 2e-2, f"t5 rel_l2 {r:.3e}"
+        out[f"L{L}"] = r
+    return out
+
+
+def check_pipeline_encode_text():
+    """encode_text of both pipelines on tiny encoders + a synthetic CLIP vocabulary and a sentencepiece model trained
+    on the spot, vs the oracle encoders on the same tokens; then generate_image from a prompt string."""
+    import tempfile
+
+    import sentencepiece as spm
+
+    from diffusionkit_b200.config import CLIPTextModelConfig, T5EncoderConfig
+    from diffusionkit_b200.text_encoders import clip_param_specs, t5_param_specs
+    from diffusionkit_b200.tokenizer import load_t5_tokenizer, load_tokenizer
+    from oracle.text_ref import CLIPTextModelRef, T5EncoderRef, tokenize_pair
+    from tests.test_text_cpu import _WORDS, _synthetic_clip_vocab
+
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        import pathlib
+
+        vf, mf, vocab = _synthetic_clip_vocab(pathlib.Path(d))
+        corpus = os.path.join(d, "corpus.txt")
+        with open(corpus, "w") as f:
+            for i in range(200):
+                f.write(" ".join(_WORDS[(i + j) % len(_WORDS)] for j in range(6)) + "\n")
+        spm.SentencePieceTrainer.train(input=corpus, model_prefix=os.path.join(d, "spiece"), vocab_size=64,
+                                       model_type="unigram", pad_id=0, eos_id=1, unk_id=2, bos_id=-1,
+                                       character_coverage=1.0, hard_vocab_limit=False, minloglevel=2)
+        tok_l = load_tokenizer(vf, mf, pad_with_eos=True)
+        tok_g = load_tokenizer(vf, mf, pad_with_eos=False)
+        V = len(vocab)
+        cl = CLIPTextModelConfig(num_layers=2, model_dims=128, num_heads=2, vocab_size=V, projection_dim=None)
+        cg = CLIPTextModelConfig(num_layers=3, model_dims=192, num_heads=3, vocab_size=V, projection_dim=192,
+                                 hidden_act="gelu")
+        t5c = T5EncoderConfig(vocab_size=256, d_model=4096, d_kv=64, d_ff=256, num_layers=2, num_heads=2)
+        pl = init_params(clip_param_specs(cl), seed=31, dtype=torch.float32)
+        pg = init_params(clip_param_specs(cg), seed=32, dtype=torch.float32)
+        pt = init_params(t5_param_specs(t5c), seed=33, dtype=torch.float32)
+        pt["wte.weight"] *= 50.0
+        prompt, negative = "a photo of the astronaut riding a horse on mars!", "cats"
+        for kind in ("sd3", "flux"):
+            if kind == "sd3":
+                cfg = replace(tiny_sd3_config(), pooled_text_embed_dim=128 + 192, token_level_text_embed_dim=4096)
+                pipe = dk.DiffusionPipeline(w16=True, a16=True, shift=3.0, mmdit_config=cfg)
+                t5_len = 512
+            else:
+                cfg = replace(tiny_flux_config(), pooled_text_embed_dim=128, token_level_text_embed_dim=4096)
+                pipe = dk.FluxPipeline(w16=True, a16=True, mmdit_config=cfg)
+                t5_len = 256
+            dt = pipe.dtype
+            tok_t5 = load_t5_tokenizer(os.path.join(d, "spiece.model"), t5_len)
+            try:
+                pipe.encode_text(prompt)
+                raise RuntimeError("encode_text without encoders should refuse")
+            except dk.DkError:
+                pass
+            pipe.load_text_encoders(clip_l={k: v.to(dt) for k, v in pl.items()}, clip_g={k: v.to(dt) for k, v in pg.items()},
+                                    t5={k: v.to(torch.bfloat16) for k, v in pt.items()}, tokenizer_l=tok_l,
+                                    tokenizer_g=tok_g, t5_tokenizer=tok_t5, clip_l_config=cl, clip_g_config=cg,
+                                    t5_config=t5c)
+            cond, pooled = pipe.encode_text(prompt, cfg_weight=5.0, negative_text=negative)
+            # oracle on the same tokens, weights rounded like the device copies
+            ref_l = CLIPTextModelRef({k: v.to(dt).float() for k, v in pl.items()}, cl.num_layers, cl.num_heads, cl.hidden_act)
+            ref_g = CLIPTextModelRef({k: v.to(dt).float() for k, v in pg.items()}, cg.num_layers, cg.num_heads, cg.hidden_act)
+            ref_t = T5EncoderRef({k: v.to(torch.bfloat16).float() for k, v in pt.items()}, t5c.num_layers, t5c.num_heads)
+            tl, tg, tt = [tokenize_pair(t, prompt, negative) for t in (tok_l, tok_g, tok_t5)]
+            if kind == "sd3":
+                pl_o, _, hl = ref_l(tl)
+                pg_o, _, hg = ref_g(tg)
+                c = torch.cat([hl[-2], hg[-2]], dim=-1)
+                c = torch.cat([c, torch.zeros(2, 77, 4096 - c.shape[-1])], dim=-1)
+                assert tt.shape == (2, 512) and cond.shape == (2, 77 + 512, 4096) and pooled.shape == (2, 320)
+                want_c, want_p = torch.cat([c, ref_t(tt)], dim=1), torch.cat([pl_o, pg_o], dim=-1)
+            else:
+                pl_o, _, _ = ref_l(tl[[0]])
+                padded = torch.zeros((1, 256), dtype=torch.int64)
+                padded[:, : tt.shape[1]] = tt[[0]]
+                want_c, want_p = ref_t(padded), pl_o
+                assert cond.shape == (1, 256, 4096) and pooled.shape == (1, 128)
+            assert cond.dtype == pooled.dtype == pipe.activation_dtype
+            res[kind + "_cond"], res[kind + "_pooled"] = rel_l2(cond, want_c), rel_l2(pooled, want_p)
+            assert res[kind + "_cond"] <= 2e-2 and res[kind + "_pooled"] <= 2e-2, res
+            image, log = pipe.generate_image(prompt, num_steps=2, cfg_weight=5.0 if kind == "sd3" else 0.0,
+                                             negative_text=negative, latent_size=(8, 8), seed=1, verbose=False)
+            assert image.size == (64, 64) and log["text_encoding"]["time"] >= 0
+    return res
+
+
+def check_full_size_text_encoders():
+    """CLIP-L/14, OpenCLIP bigG and T5-XXL (4.7 B parameters) at their real sizes with synthetic weights: shapes,
+    determinism, finiteness, batch independence; CUDA-event times for DESIGN.md."""
+    from diffusionkit_b200.config import CLIP_G, CLIP_L, T5EncoderConfig
+    from diffusionkit_b200.text_encoders import CLIPTextModel, SD3T5Encoder, clip_param_specs, t5_param_specs
+
+    out = {}
+    gen = torch.Generator().manual_seed(9)
+
+    def timed(fn):
+        fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = fn()
+        e.record()
+        torch.cuda.synchronize()
+        return r, s.elapsed_time(e)
+
+    for name, cfg in (("clip_l", CLIP_L), ("clip_g", CLIP_G)):
+        m = CLIPTextModel(init_params(clip_param_specs(cfg), seed=41, dtype=torch.float16, device=DEV), cfg)
+        tokens = torch.randint(1, 49406, (2, 77), generator=gen)
+        tokens[:, 30] = 49407
+        o, ms = timed(lambda: m(tokens))
+        o2 = m(tokens[1:2])
+        assert o.last_hidden_state.shape == (2, 77, cfg.model_dims) and bool(torch.isfinite(o.last_hidden_state.float()).all())
+        assert o.pooled_output.shape == (2, cfg.projection_dim or cfg.model_dims)
+        assert rel_l2(o2.last_hidden_state, o.last_hidden_state[1:2]) <= 1e-5
+        out[name + "_ms"] = round(ms, 3)
+        del m
+    t5 = SD3T5Encoder(init_params(t5_param_specs(T5EncoderConfig()), seed=42, dtype=torch.bfloat16, device=DEV))
+    for L in (256, 512):
+        tokens = torch.randint(0, 32128, (2, L), generator=gen)
+        o, ms = timed(lambda: t5(tokens))
+        assert o.shape == (2, L, 4096) and bool(torch.isfinite(o.float()).all())
+        assert torch.equal(o, t5(tokens)), "T5 encoder is not deterministic"
+        assert rel_l2(t5(tokens[1:2]), o[1:2]) <= 1e-5
+        out[f"t5_xxl_L{L}_B2_ms"] = round(ms, 3)
+    return out
+
+
 def check_full_size_sd35_properties():
     """SD3.5-large at its real width/depth (SD3_8b: 38 blocks, 38 heads x 64, hidden 2432, QK-norm; 8 B synthetic
     parameters), 512x512, CFG: determinism, batch independence, finiteness."""
@@ -436,7 +616,8 @@ def check_full_size_vae_properties():
 
 
 ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_sd35_tiny, check_pipeline_q4_ckpt,
-              check_full_size_sd35_properties, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
+              check_full_size_sd35_properties, check_clip_tiny, check_t5_tiny, check_pipeline_encode_text,
+              check_full_size_text_encoders, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
               check_vae_decode_tiny, check_vae_decode_batch_fp16, check_vae_encode_tiny, check_vae_encode_batch_fp16,
               check_pipeline_img2img, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
               check_pipeline_errors, check_pipeline_local_ckpt, check_full_size_flux_properties, check_full_size_vae_properties]
