@@ -419,14 +419,20 @@ def check_t5_tiny():
     out = {}
     enc = SD3T5Encoder({k: v.to(DEV) for k, v in p16.items()}, cfg)
     ref = T5EncoderRef({k: v.float() for k, v in p16.items()}, cfg.num_layers, cfg.num_heads)
+    ref16 = T5EncoderRef({k: v.float() for k, v in p16.items()}, cfg.num_layers, cfg.num_heads, dt=torch.bfloat16)
     for (B, L) in [(2, 64), (1, 200)]:
         tokens = torch.randint(0, cfg.vocab_size, (B, L), generator=gen)
         got = enc(tokens)
         torch.cuda.synchronize()
         assert got.shape == (B, L, cfg.d_model)
-        r = rel_l2(got, ref(tokens))
-        assert r <= 2e-2, f"t5 rel_l2 {r:.3e}"
+        want = ref(tokens)
+        r = rel_l2(got, want)
+        # yardstick: the oracle run with the reference's own 16-bit rounding points (attention in bf16, t5.py:216-218)
+        # against the same oracle in fp32.  The engine has to be at least as close to fp32 as that.
+        r16 = rel_l2(ref16(tokens), want)
+        assert r <= max(2e-2, r16), f"t5 rel_l2 {r:.3e} (reference-dtype oracle: {r16:.3e})"
         out[f"L{L}"] = r
+        out[f"L{L}_reference_dtype_oracle"] = r16
     return out
 
 
