@@ -478,10 +478,12 @@ class DiffusionPipeline:
         log["decoding"]["pre"] = mem()
         latents16 = ops.cast_to_16(latents, self.activation_dtype)          # latents.astype(activation_dtype) (:459)
         _, u8 = self._decode(latents16, want_u8=True)
-        host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+        host = getattr(self, "_host_u8", None)                              # pinned staging, reused across calls
+        if host is None or host.shape != u8.shape:
+            host = self._host_u8 = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
         host.copy_(u8, non_blocking=True)                                   # device -> host: the result
         torch.cuda.current_stream().synchronize()
-        images_u8 = host.numpy()
+        images_u8 = host.numpy().copy()                                     # the staging buffer is reused next call
         log["decoding"]["post"] = mem()
         log["decoding"]["time"] = round(time.time() - t0, 3)
         log["peak_memory"] = max(log["peak_memory"], log["decoding"]["post"]["peak_memory"])
@@ -499,7 +501,9 @@ class DiffusionPipeline:
         # MT19937 stream as the seeded global generator, without the global state (thread-safe for batches).
         shape = tuple(x_T.shape)
         noise = np.random.RandomState(seed).randn(shape[0], shape[3], shape[1], shape[2])
-        return torch.from_numpy(noise).permute(0, 2, 3, 1).to(torch.float32).contiguous()
+        # float64 -> float32 and NCHW -> NHWC in numpy: the same values as mx.array(noise).transpose(0, 2, 3, 1), and
+        # ~100x cheaper on a many-core host than a strided multi-threaded torch CPU copy
+        return torch.from_numpy(np.ascontiguousarray(noise.astype(np.float32).transpose(0, 2, 3, 1)))
 
     def _get_noise_batch(self, seeds, x_T):
         if len(seeds) == 1:
