@@ -483,7 +483,7 @@ class DiffusionPipeline:
             host = self._host_u8 = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
         host.copy_(u8, non_blocking=True)                                   # device -> host: the result
         torch.cuda.current_stream().synchronize()
-        images_u8 = host.numpy().copy()                                     # the staging buffer is reused next call
+        images_u8 = host.numpy()         # Image.fromarray copies RGB data, so reusing the staging buffer is safe
         log["decoding"]["post"] = mem()
         log["decoding"]["time"] = round(time.time() - t0, 3)
         log["peak_memory"] = max(log["peak_memory"], log["decoding"]["post"]["peak_memory"])
