@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc failed")
     if procs or not os.path.exists(LIB):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
+        cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs, "-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -32,14 +32,16 @@ template <int G2_BN>
 struct G2Cfg {
   static constexpr int STAGES = G2_BN == 256 ? 6 : (G2_BN == 192 ? 7 : 8);
   static constexpr int B_BYTES = (G2_BN / 2) * G2_BK * 2;
-  static constexpr int SMEM_BYTES = STAGES * (G2_A_BYTES + B_BYTES) + 256 + 1024;
+  static constexpr int STG_BYTES = 8 * 32 * 128;    // TMA-store epilogue: 32 rows x 64 columns per epilogue warp
+  static constexpr bool TMA_STORE_OK = G2_BN % 128 == 0;      // every warp owns whole 64-column chunks
+  static constexpr int SMEM_BYTES = STAGES * (G2_A_BYTES + B_BYTES) + (TMA_STORE_OK ? STG_BYTES : 0) + 256 + 1024;
   static constexpr int TMEM_COLS = G2_BN > 128 ? 512 : 256;   // two accumulators, power-of-two allocation
 };
 
 template <typename T, int G2_BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
-gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape s,
-                const GemmEpi e) {
+gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmOut, const GemmShape s, const GemmEpi e, const int tma_store) {
   using H16 = Half16<T>;
   constexpr int G2_STAGES = G2Cfg<G2_BN>::STAGES;
   constexpr int G2_B_BYTES = G2Cfg<G2_BN>::B_BYTES;
@@ -48,7 +50,9 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + G2_STAGES * G2_A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_STAGES * (G2_A_BYTES + G2_B_BYTES));
+  constexpr int G2_STG_BYTES = G2Cfg<G2_BN>::TMA_STORE_OK ? G2Cfg<G2_BN>::STG_BYTES : 0;
+  uint8_t* sStg = smem + G2_STAGES * (G2_A_BYTES + G2_B_BYTES);   // 1024-aligned: every stage is a multiple of 1 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStg + G2_STG_BYTES);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tfull_bar = empty_bar + G2_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -65,6 +69,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (tma_store) tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < G2_STAGES; ++i) {
@@ -189,8 +194,17 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_leader);
       };
+      if constexpr (G2Cfg<G2_BN>::TMA_STORE_OK) {
+        if (tma_store) {
+          gemm_epilogue_drain_tma<T, NCH>(s, e, t_row, n_half0, row_ok, rrow, batch,
+                                          smem_u32(sStg) + (warp - 4) * (32 * 128), &tmOut,
+                                          m_blk * 256 + static_cast<int>(rank) * G2_BM + quarter * 32, release_acc);
+          continue;
+        }
+      }
       gemm_epilogue_drain<T, NCH, 0>(s, e, t_row, n_half0, row_ok, orow, rrow, batch, pos, release_acc);
     }
+    if (tma_store && lane == 0) tma_store_wait_all();   // bulk stores complete before the CTA retires
   }
 
   // nobody leaves while the peer may still signal its barriers or read its shared memory
@@ -203,8 +217,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 template <typename T, int G2_BN>
-static int launch_gemm2(dk_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmShape& s,
-                        const GemmEpi& e, cudaStream_t stream) {
+static int launch_gemm2(dk_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut,
+                        int tma_store, const GemmShape& s, const GemmEpi& e, cudaStream_t stream) {
   auto kern = gemm2_tc_kernel<T, G2_BN>;
   static bool configured = false;
   if (!configured) {
@@ -214,7 +228,7 @@ static int launch_gemm2(dk_ctx* ctx, const CUtensorMap& tmA, const CUtensorMap& 
   const int total = s.num_m * s.num_n;
   const int max_pairs = ctx->sm_count / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
-  kern<<<2 * pairs, G2_THREADS, G2Cfg<G2_BN>::SMEM_BYTES, stream>>>(tmA, tmB, s, e);
+  kern<<<2 * pairs, G2_THREADS, G2Cfg<G2_BN>::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, s, e, tma_store);
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -271,12 +285,27 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
     const uint32_t box[2] = {G2_BK, static_cast<uint32_t>(bn / 2)};
     if (int rc = dk_make_tmap_16b(ctx, &tmB, W, 2, dims, strides, box)) return rc;
   }
-  if (dtype == DK_BF16) {
-    if (bn == 256) return launch_gemm2<__nv_bfloat16, 256>(ctx, tmA, tmB, s, e, stream);
-    if (bn == 192) return launch_gemm2<__nv_bfloat16, 192>(ctx, tmA, tmB, s, e, stream);
-    return launch_gemm2<__nv_bfloat16, 128>(ctx, tmA, tmB, s, e, stream);
+  // TMA-store epilogue: identity-mapped, 16-byte aligned outputs without the fused QK path
+  static const int tma_store_mode = [] {
+    const char* v = getenv("DK_GEMM_TMA_STORE");
+    return v ? atoi(v) : 1;
+  }();
+  CUtensorMap tmOut = tmA;   // placeholder when unused (the kernel never touches it then)
+  int tma_store = 0;
+  if (tma_store_mode != 0 && bn != 192 && e.qk_d == 0 && e.out_batch_rows == e.rpb && e.out_row_off == 0 &&
+      (e.ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15u) == 0) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(e.ldc) * 2};
+    const uint32_t box[2] = {64, 32};
+    if (int rc = dk_make_tmap_16b(ctx, &tmOut, e.out, 2, dims, strides, box)) return rc;
+    tma_store = 1;
   }
-  if (bn == 256) return launch_gemm2<__half, 256>(ctx, tmA, tmB, s, e, stream);
-  if (bn == 192) return launch_gemm2<__half, 192>(ctx, tmA, tmB, s, e, stream);
-  return launch_gemm2<__half, 128>(ctx, tmA, tmB, s, e, stream);
+  if (dtype == DK_BF16) {
+    if (bn == 256) return launch_gemm2<__nv_bfloat16, 256>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
+    if (bn == 192) return launch_gemm2<__nv_bfloat16, 192>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
+    return launch_gemm2<__nv_bfloat16, 128>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
+  }
+  if (bn == 256) return launch_gemm2<__half, 256>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
+  if (bn == 192) return launch_gemm2<__half, 192>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
+  return launch_gemm2<__half, 128>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
 }

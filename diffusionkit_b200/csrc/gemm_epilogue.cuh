@@ -248,4 +248,99 @@ for (int chunk = 0; chunk < NCH; ++chunk) {
 }
 }
 
+// Same arithmetic as the generic path of gemm_epilogue_drain, but the finished 16-bit tile leaves through shared
+// memory and TMA: each warp packs 32 rows x 64 columns into its own 4 KB staging buffer (128B-swizzled rows, so the
+// 16-byte st.shared of the 32 lanes are conflict free) and one lane issues a single bulk tensor store for it — whole
+// 128-byte lines per request instead of one 32-byte sector per thread.  Only for identity-mapped outputs (row m of the
+// tile grid is row m of `out`); rows/columns beyond M/N are clipped by the tensor map.
+//   stg: this warp's staging buffer (shared::cta address, 1024-byte aligned);  out_row0: output row of lane 0
+//   NCH: 32-column chunks owned by this warp (even).
+template <typename T, int NCH, typename Release>
+__device__ __forceinline__ void gemm_epilogue_drain_tma(const GemmShape& s, const GemmEpi& e, uint32_t t_row, int n_half0,
+                                                        bool row_ok, long long rrow, int batch, uint32_t stg,
+                                                        const CUtensorMap* tm_out, int out_row0, Release release_acc) {
+  using H16 = Half16<T>;
+  static_assert(NCH % 2 == 0, "TMA-store epilogue works on 64-column chunks");
+  const T* bias = reinterpret_cast<const T*>(e.bias);
+  const T* gate = reinterpret_cast<const T*>(e.gate);
+  const T* res = reinterpret_cast<const T*>(e.res);
+  const int lane = threadIdx.x & 31;
+  const uint32_t my_row = stg + lane * 128;
+#pragma unroll 1
+  for (int c64 = 0; c64 < NCH / 2; ++c64) {
+    const int n64 = n_half0 + c64 * 64;
+    // the previous store out of this buffer must have finished reading it
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      uint32_t r[32];
+      tmem_ld_32x32(t_row + c64 * 64 + hlf * 32, r);
+      tmem_ld_wait();
+      if (c64 == NCH / 2 - 1 && hlf == 1) release_acc();
+      const int n0 = n64 + hlf * 32;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + j * 8;
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j * 8 + i]);
+        if (row_ok && n < s.N && e.debug < 2) {
+          if (bias != nullptr) {
+            const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n);
+            const uint32_t bw[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = H16::unpack(bw[i]);
+              v[2 * i] += f.x;
+              v[2 * i + 1] += f.y;
+            }
+          }
+          if (e.act == DK_ACT_GELU_ERF) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+          } else if (e.act == DK_ACT_SILU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+          } else if (e.act == DK_ACT_QUICK_GELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = quick_gelu_f(v[i]);
+          }
+          if (gate != nullptr) {
+            const uint4 g4 = *reinterpret_cast<const uint4*>(gate + static_cast<long long>(batch) * e.gate_ld + n);
+            const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = H16::unpack(gw[i]);
+              v[2 * i] *= f.x;
+              v[2 * i + 1] *= f.y;
+            }
+          }
+          if (res != nullptr) {
+            const uint4 r4 = *reinterpret_cast<const uint4*>(res + rrow * e.ldres + n);
+            const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = H16::unpack(rw[i]);
+              v[2 * i] += f.x;
+              v[2 * i + 1] += f.y;
+            }
+          }
+        }
+        const int ch = hlf * 4 + j;   // 16-byte chunk inside the 128-byte row
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((ch ^ (lane & 7)) << 4)),
+                     "r"(H16::pack(v[0], v[1])), "r"(H16::pack(v[2], v[3])), "r"(H16::pack(v[4], v[5])),
+                     "r"(H16::pack(v[6], v[7]))
+                     : "memory");
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && e.debug == 0 && n64 < s.N) {
+      tma_store_2d(tm_out, stg, n64, out_row0);
+      tma_store_commit();
+    }
+  }
+}
+
 }  // namespace dk

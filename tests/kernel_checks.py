@@ -472,7 +472,39 @@ def check_gemm_pair_kernel():
     out["remap"] = _gemm_case(600, 512, 256, torch.bfloat16, bias=True, gate=True, res=True, remap=True,
                               name="pair_remap")
     out["fp16"] = _gemm_case(300, 512, 320, torch.float16, bias=True, name="pair_fp16")
+    out.update(_pair_store_cases())
     out.update({"qk_" + k: v for k, v in check_gemm_fused_qk_norm_rope().items()})
+    return out
+
+
+def _pair_store_cases():
+    """outputs the TMA-store epilogue has to get right: a strided column window of a wider buffer (the FLUX single-block
+    concat buffer), rows/columns that are not tile multiples next to data that must survive, in-place residual"""
+    out = {}
+    M, N, K, ld, c0 = 1000, 520, 256, 1024, 256
+    A, W = _rand((M, K), torch.bfloat16), _rand((N, K), torch.bfloat16, 1 / math.sqrt(K))
+    buf = torch.full((M + 8, ld), 7.0, dtype=torch.bfloat16, device=DEV)
+    view = buf[:M, c0:c0 + N]
+    ops.gemm(A, W, out=view, act=ACT_GELU_ERF)
+    out["window"] = _assert_close("pair_window", view, torch.nn.functional.gelu(A.float() @ W.float().t()), 4e-3)
+    keep = buf.clone()
+    keep[:M, c0:c0 + N] = 7.0
+    assert bool((keep == 7.0).all()), "pair_window: bytes outside the output window were written"
+    x = _rand((M, N), torch.bfloat16)
+    g = _rand((1, N), torch.bfloat16)
+    ref = x.float() + g.float() * (A.float() @ W.float().t())
+    out["inplace"] = _assert_close("pair_inplace", ops.gemm(A, W, out=x, res=x, gate=g), ref, 4e-3)
+    return out
+
+
+def check_gemm_pair_legacy_store():
+    """the register -> global store path of the pair kernel (DK_GEMM_TMA_STORE=0) stays correct"""
+    os.environ["DK_GEMM_PAIR"] = "2"
+    os.environ["DK_GEMM_TMA_STORE"] = "0"
+    _setup()
+    out = {"large": _gemm_case(2048, 1536, 512, torch.bfloat16, bias=True, gate=True, res=True, name="pairleg_large"),
+           "ragged": _gemm_case(300, 264, 200, torch.bfloat16, name="pairleg_ragged")}
+    out.update(_pair_store_cases())
     return out
 
 
@@ -676,7 +708,7 @@ def check_error_paths():
 ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
     check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
-    check_gemm_pair_kernel, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
+    check_gemm_pair_kernel, check_gemm_pair_legacy_store, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
     check_text_kernels, check_attention_small,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
     check_attention_v1_kernel, check_attention_v2_kernel,

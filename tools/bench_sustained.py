@@ -64,14 +64,17 @@ def main():
         for (A, Ws, out) in bufs:
             torch.matmul(A, Ws[i % NW].t(), out=out)
 
-    for name, fn in [("ours", ours), ("cublas", cublas), ("ours_again", ours)]:
-        it, sec, clocks = run(fn, 500)
+    legs = [("ours", ours), ("cublas", cublas), ("ours_again", ours)]
+    if os.environ.get("BS_ONLY_OURS"):
+        legs = [("ours", ours)]
+    for name, fn in legs:
+        it, sec, clocks = run(fn, int(os.environ.get("BS_ITERS", "500")))
         mhz = sorted(c[0] for c in clocks)[len(clocks) // 2]
         watts = sorted(c[1] for c in clocks)[len(clocks) // 2]
         res[name] = {"tflops": flops_seq * it / sec / 1e12, "sm_mhz_median": mhz, "power_w_median": watts, "iters": it}
         print(name, res[name], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    tag = os.environ.get("DK_GEMM_PAIR", "1")
+    tag = os.environ.get("DK_GEMM_PAIR", "1") + "_tmastore" + os.environ.get("DK_GEMM_TMA_STORE", "1")
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"bench_sustained_pair{tag}.json"), "w"), indent=1)
 
 
