@@ -41,7 +41,11 @@ struct G2Cfg {
 template <typename T, int G2_BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmOut, const GemmShape s, const GemmEpi e, const int tma_store) {
+                const __grid_constant__ CUtensorMap tmOut, const GemmShape s, const GemmEpi e, const int flags) {
+  const int tma_store = flags & 1;
+  // timing experiment only (DK_GEMM_DEBUG_HALF_B): each CTA fetches half of its W rows, i.e. the L2 traffic a 4-CTA
+  // cluster with multicast W tiles would have; results are garbage
+  const uint32_t b_tx_bytes = (flags & 2) ? G2Cfg<G2_BN>::B_BYTES / 2 : G2Cfg<G2_BN>::B_BYTES;
   using H16 = Half16<T>;
   constexpr int G2_STAGES = G2Cfg<G2_BN>::STAGES;
   constexpr int G2_B_BYTES = G2Cfg<G2_BN>::B_BYTES;
@@ -117,7 +121,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait_warp(&empty_bar[stage], phase ^ 1);
         if (elect_one_sync()) {
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          mbar_arrive_expect_tx_cluster(full_leader, G2_A_BYTES + G2_B_BYTES);
+          mbar_arrive_expect_tx_cluster(full_leader, G2_A_BYTES + b_tx_bytes);
           tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, full_leader, kb * G2_BK, a_row);
           tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, full_leader, kb * G2_BK, b_row);
         }
@@ -273,6 +277,7 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
   s.num_n = dk_ceil_div(N, bn);
   s.num_k = dk_ceil_div(K, G2_BK);
   CUtensorMap tmA, tmB;
+  int dbg_flags = 0;
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(lda) * 2};
@@ -282,7 +287,12 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {G2_BK, static_cast<uint32_t>(bn / 2)};
+    static const int half_b = [] {
+      const char* v = getenv("DK_GEMM_DEBUG_HALF_B");
+      return v ? atoi(v) : 0;
+    }();
+    dbg_flags = half_b ? 2 : 0;
+    const uint32_t box[2] = {G2_BK, static_cast<uint32_t>(half_b ? bn / 4 : bn / 2)};
     if (int rc = dk_make_tmap_16b(ctx, &tmB, W, 2, dims, strides, box)) return rc;
   }
   // TMA-store epilogue: identity-mapped, 16-byte aligned outputs without the fused QK path
@@ -300,6 +310,7 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
     if (int rc = dk_make_tmap_16b(ctx, &tmOut, e.out, 2, dims, strides, box)) return rc;
     tma_store = 1;
   }
+  tma_store |= dbg_flags;
   if (dtype == DK_BF16) {
     if (bn == 256) return launch_gemm2<__nv_bfloat16, 256>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
     if (bn == 192) return launch_gemm2<__nv_bfloat16, 192>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
