@@ -286,8 +286,8 @@ def check_pipeline_errors():
         pass
     try:
         pipe.encode_text("a prompt")
-        raise RuntimeError("encode_text should be NotImplemented")
-    except NotImplementedError:
+        raise RuntimeError("encode_text without attached encoders should refuse")
+    except dk.DkError:
         pass
     try:
         pipe.mmdit(torch.zeros(1, 8, 16, dtype=torch.bfloat16, device=DEV), cond.to(DEV), 0.0)
