@@ -55,6 +55,21 @@ def mmdit_flops_per_forward(cfg, n_img, n_txt):
     return total
 
 
+def committed_gemm_traffic():
+    """dram__bytes_read + dram__bytes_write of ONE launch of the dominant kernel (gemm2_tc_kernel on the largest C4
+    shape, 16384 x 12288 x 3072 + GELU) from the committed `ncu --set full` capture; algorithmic bytes of that launch are
+    (16384 + 12288) * 3072 * 2 + 16384 * 12288 * 2 = 579 MB."""
+    try:
+        rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.json")))
+        for r in rows:
+            if "gemm2_tc_kernel" in r.get("Kernel Name []", ""):
+                mb = float(r["dram__bytes_read.sum [Mbyte]"]) + float(r["dram__bytes_write.sum [Mbyte]"])
+                return mb * 1e6, "profiles/r01_ncu_full_final.json: gemm2_tc_kernel 16384x12288x3072, bytes per launch"
+    except Exception:
+        pass
+    return None, None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -347,7 +362,8 @@ def run_ours(args):
         "roofline": {"bound": "tensor",
                      "kernel": "gemm2_tc_kernel / gemm_tc_kernel (tcgen05 GEMMs: every nn.Linear of the MMDiT)",
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                     "frac": achieved / peaks["bf16_tflops"], "traffic": committed_gemm_traffic()[0],
+                     "traffic_source": committed_gemm_traffic()[1],
                      "peak_source": f"{peaks['source']} bf16 burst (sustained {peaks['bf16_tflops_sustained']})",
                      "launches_timed": n_gemm, "gemm_seconds_of_one_step": t_gemm},
         "mmdit_tensor_frac_sustained": mmdit_frac,
