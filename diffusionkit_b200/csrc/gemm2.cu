@@ -202,7 +202,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (tma_store) {
           gemm_epilogue_drain_tma<T, NCH>(s, e, t_row, n_half0, row_ok, rrow, batch,
                                           smem_u32(sStg) + (warp - 4) * (32 * 128), &tmOut,
-                                          m_blk * 256 + static_cast<int>(rank) * G2_BM + quarter * 32, release_acc);
+                                          m_blk * 256 + static_cast<int>(rank) * G2_BM + quarter * 32, (flags & 4) == 0,
+                                          release_acc);
           continue;
         }
       }
@@ -308,7 +309,7 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
     const uint64_t strides[1] = {static_cast<uint64_t>(e.ldc) * 2};
     const uint32_t box[2] = {64, 32};
     if (int rc = dk_make_tmap_16b(ctx, &tmOut, e.out, 2, dims, strides, box)) return rc;
-    tma_store = 1;
+    tma_store = tma_store_mode == 2 ? 5 : 1;   // DK_GEMM_TMA_STORE=2: without the L2 evict-first hint (A/B only)
   }
   tma_store |= dbg_flags;
   if (dtype == DK_BF16) {

@@ -258,9 +258,13 @@ for (int chunk = 0; chunk < NCH; ++chunk) {
 template <typename T, int NCH, typename Release>
 __device__ __forceinline__ void gemm_epilogue_drain_tma(const GemmShape& s, const GemmEpi& e, uint32_t t_row, int n_half0,
                                                         bool row_ok, long long rrow, int batch, uint32_t stg,
-                                                        const CUtensorMap* tm_out, int out_row0, Release release_acc) {
+                                                        const CUtensorMap* tm_out, int out_row0, bool evict_first,
+                                                        Release release_acc) {
   using H16 = Half16<T>;
   static_assert(NCH % 2 == 0, "TMA-store epilogue works on 64-column chunks");
+  // the output is consumed by a later kernel, the operand tiles by this one: without the hint the 400 MB of C lines
+  // of a large GEMM push A/W out of L2 (ncu: hit rate 91 % -> 83 %, DRAM reads 459 -> 738 MB per launch)
+  const uint64_t policy = l2_policy_evict_first();
   const T* bias = reinterpret_cast<const T*>(e.bias);
   const T* gate = reinterpret_cast<const T*>(e.gate);
   const T* res = reinterpret_cast<const T*>(e.res);
@@ -337,7 +341,10 @@ __device__ __forceinline__ void gemm_epilogue_drain_tma(const GemmShape& s, cons
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && e.debug == 0 && n64 < s.N) {
-      tma_store_2d(tm_out, stg, n64, out_row0);
+      if (evict_first)
+        tma_store_2d_hint(tm_out, stg, n64, out_row0, policy);
+      else
+        tma_store_2d(tm_out, stg, n64, out_row0);
       tma_store_commit();
     }
   }
