@@ -30,10 +30,10 @@ constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;          // 16 KB
 // 256-wide tile count is a poor multiple of the 74 CTA pairs (N = 3072: 10.4 waves) can be re-tiled (192: 13.8 waves).
 template <int G2_BN>
 struct G2Cfg {
-  static constexpr int STAGES = G2_BN == 256 ? 6 : (G2_BN == 192 ? 7 : 8);
+  static constexpr int STAGES = G2_BN == 256 ? 6 : (G2_BN == 192 ? 6 : 8);   // 192: 6 x 28 KB + the 32 KB staging
   static constexpr int B_BYTES = (G2_BN / 2) * G2_BK * 2;
   static constexpr int STG_BYTES = 8 * 32 * 128;    // TMA-store epilogue: 32 rows x 64 columns per epilogue warp
-  static constexpr bool TMA_STORE_OK = G2_BN % 128 == 0;      // every warp owns whole 64-column chunks
+  static constexpr bool TMA_STORE_OK = true;   // 64-column chunks: 256 -> 2+2 per warp pair, 192 -> 2+1, 128 -> 1+1
   static constexpr int SMEM_BYTES = STAGES * (G2_A_BYTES + B_BYTES) + (TMA_STORE_OK ? STG_BYTES : 0) + 256 + 1024;
   static constexpr int TMEM_COLS = G2_BN > 128 ? 512 : 256;   // two accumulators, power-of-two allocation
 };
@@ -54,7 +54,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + G2_STAGES * G2_A_BYTES;
-  constexpr int G2_STG_BYTES = G2Cfg<G2_BN>::TMA_STORE_OK ? G2Cfg<G2_BN>::STG_BYTES : 0;
+  constexpr int G2_STG_BYTES = G2Cfg<G2_BN>::STG_BYTES;
   uint8_t* sStg = smem + G2_STAGES * (G2_A_BYTES + G2_B_BYTES);   // 1024-aligned: every stage is a multiple of 1 KB
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStg + G2_STG_BYTES);
   uint64_t* empty_bar = full_bar + G2_STAGES;
@@ -198,14 +198,23 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_leader);
       };
-      if constexpr (G2Cfg<G2_BN>::TMA_STORE_OK) {
-        if (tma_store) {
-          gemm_epilogue_drain_tma<T, NCH>(s, e, t_row, n_half0, row_ok, rrow, batch,
-                                          smem_u32(sStg) + (warp - 4) * (32 * 128), &tmOut,
-                                          m_blk * 256 + static_cast<int>(rank) * G2_BM + quarter * 32, (flags & 4) == 0,
+      if (tma_store) {
+        const uint32_t stg = smem_u32(sStg) + (warp - 4) * (32 * 128);
+        const int out_row0 = m_blk * 256 + static_cast<int>(rank) * G2_BM + quarter * 32;
+        const bool hint = (flags & 4) == 0;
+        if constexpr (G2_BN == 192) {
+          // 192 columns = three 64-column chunks: the first warpgroup takes two, the second one
+          const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * G2_BN + half * 128;
+          const int n0 = n_blk * G2_BN + half * 128;
+          if (half == 0)
+            gemm_epilogue_drain_tma<T, 4>(s, e, t0, n0, row_ok, rrow, batch, stg, &tmOut, out_row0, hint, release_acc);
+          else
+            gemm_epilogue_drain_tma<T, 2>(s, e, t0, n0, row_ok, rrow, batch, stg, &tmOut, out_row0, hint, release_acc);
+        } else {
+          gemm_epilogue_drain_tma<T, NCH>(s, e, t_row, n_half0, row_ok, rrow, batch, stg, &tmOut, out_row0, hint,
                                           release_acc);
-          continue;
         }
+        continue;
       }
       gemm_epilogue_drain<T, NCH, 0>(s, e, t_row, n_half0, row_ok, orow, rrow, batch, pos, release_acc);
     }
@@ -303,7 +312,7 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
   }();
   CUtensorMap tmOut = tmA;   // placeholder when unused (the kernel never touches it then)
   int tma_store = 0;
-  if (tma_store_mode != 0 && bn != 192 && e.qk_d == 0 && e.out_batch_rows == e.rpb && e.out_row_off == 0 &&
+  if (tma_store_mode != 0 && e.qk_d == 0 && e.out_batch_rows == e.rpb && e.out_row_off == 0 &&
       (e.ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15u) == 0) {
     const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(e.ldc) * 2};
