@@ -308,17 +308,19 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
   // TMA-store epilogue: identity-mapped, 16-byte aligned outputs without the fused QK path
   static const int tma_store_mode = [] {
     const char* v = getenv("DK_GEMM_TMA_STORE");
-    return v ? atoi(v) : 1;
+    return v ? atoi(v) : 3;
   }();
+  // modes: 0 register stores; 1 TMA stores with the L2 evict-first hint, all tile widths; 2 same without the hint;
+  //        3 (default: the configuration validated on hardware) no hint, 256/128-wide tiles only
   CUtensorMap tmOut = tmA;   // placeholder when unused (the kernel never touches it then)
   int tma_store = 0;
-  if (tma_store_mode != 0 && e.qk_d == 0 && e.out_batch_rows == e.rpb && e.out_row_off == 0 &&
+  if (tma_store_mode != 0 && !(tma_store_mode == 3 && bn == 192) && e.qk_d == 0 && e.out_batch_rows == e.rpb && e.out_row_off == 0 &&
       (e.ldc * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15u) == 0) {
     const uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
     const uint64_t strides[1] = {static_cast<uint64_t>(e.ldc) * 2};
     const uint32_t box[2] = {64, 32};
     if (int rc = dk_make_tmap_16b(ctx, &tmOut, e.out, 2, dims, strides, box)) return rc;
-    tma_store = tma_store_mode == 2 ? 5 : 1;   // DK_GEMM_TMA_STORE=2: without the L2 evict-first hint (A/B only)
+    tma_store = tma_store_mode == 1 ? 1 : 5;   // bit 2: no cache hint
   }
   tma_store |= dbg_flags;
   if (dtype == DK_BF16) {
