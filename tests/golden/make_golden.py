@@ -79,6 +79,23 @@ def tiny_vectors():
     img = decode_latents_to_image(VAEDecoderRef(vp), z)
     np.savez_compressed(os.path.join(HERE, "tiny_vae_decode.npz"), latent=z.numpy(), image=img.numpy())
     out["vae"] = float(img.mean())
+    # VAE encoder + img2img posterior sample, reduced widths to keep the fixture small
+    from diffusionkit_b200.config import VAEEncoderConfig
+    from diffusionkit_b200.weights import vae_encoder_param_specs
+    from oracle.vae_ref import VAEEncoderRef, encode_image_to_latents, read_image_array
+    from oracle.sampler_ref import get_noise
+
+    ecfg = VAEEncoderConfig(block_out_channels=(32, 64, 64, 64), layers_per_block=1)
+    ep = init_params(vae_encoder_param_specs(ecfg), seed=9, dtype=torch.float32)
+    rng = np.random.RandomState(5)
+    img_u8 = rng.randint(0, 256, (32, 48, 3), dtype=np.uint8)
+    enc = VAEEncoderRef(ep, None, ecfg.block_out_channels, ecfg.layers_per_block)
+    x = read_image_array(torch.from_numpy(img_u8))
+    hidden = enc(x)
+    z = encode_image_to_latents(enc, x, get_noise(3, 4, 6))
+    np.savez_compressed(os.path.join(HERE, "tiny_vae_encode.npz"), image_u8=img_u8, hidden=hidden.numpy(),
+                        latent_seed3=z.numpy())
+    out["vae_encode"] = float(hidden.abs().mean())
     return out
 
 

@@ -171,3 +171,29 @@ def test_q4_oracle_layout_and_roundtrip():
     kat = qr.dequantize_q4(np.array([[0x76543210]], dtype=np.uint32), np.array([[0.5]], np.float32),
                            np.array([[-1.0]], np.float32), group_size=8)
     assert kat.tolist() == [[-1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0, 2.5]]
+
+
+def test_oracle_vae_encoder_matches_golden():
+    """encoder stack (stride-2 downsample with bottom/right pad), read_image scaling and the seeded posterior sample"""
+    from diffusionkit_b200.config import VAEEncoderConfig
+    from diffusionkit_b200.weights import init_params, vae_encoder_param_specs
+    from oracle.sampler_ref import get_noise
+    from oracle.vae_ref import VAEEncoderRef, conv3x3_s2, encode_image_to_latents, read_image_array
+
+    g = _load("tiny_vae_encode.npz")
+    ecfg = VAEEncoderConfig(block_out_channels=(32, 64, 64, 64), layers_per_block=1)
+    ep = init_params(vae_encoder_param_specs(ecfg), seed=9, dtype=torch.float32)
+    enc = VAEEncoderRef(ep, None, ecfg.block_out_channels, ecfg.layers_per_block)
+    x = read_image_array(torch.from_numpy(g["image_u8"]))
+    assert float(x.min()) >= -1.0 and float(x.max()) <= 1.0 and x.shape == (1, 32, 48, 3)
+    hidden = enc(x)
+    assert hidden.shape == (1, 4, 6, 32)
+    assert torch.allclose(hidden, torch.from_numpy(g["hidden"]), atol=1e-5, rtol=1e-4)
+    z = encode_image_to_latents(enc, x, get_noise(3, 4, 6))
+    assert torch.allclose(z, torch.from_numpy(g["latent_seed3"]), atol=1e-5, rtol=1e-4)
+    # the downsample really pads bottom/right only: output (i, j) sees input rows 2i..2i+2, the last one zero-padded
+    xs = torch.arange(16.0).reshape(1, 4, 4, 1)
+    w = torch.zeros(1, 3, 3, 1)
+    w[0, 2, 2, 0] = 1.0                                   # picks input (2i + 2, 2j + 2)
+    y = conv3x3_s2(xs, w, torch.zeros(1))
+    assert y.reshape(2, 2).tolist() == [[10.0, 0.0], [0.0, 0.0]]
