@@ -983,7 +983,11 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 constexpr int ATT3_THREADS = 576;
 
 // POLY4: of every four exponentials, how many run on the FMA pipe (ex2_poly) instead of MUFU.EX2 (0, 1 or 2)
-template <typename T, int D, int POLY4>
+// VAR 1 (DK_ATTENTION_IMPL=3b, experimental, not yet measured): the two threads that share a row synchronise through a
+// 64-thread named barrier of their own (one per TMEM lane quarter and Q tile) instead of the tile-wide 256-thread one.
+// Same arithmetic in the same order as VAR 0.  (Keeping the 64 scores in registers between the two passes was tried
+// at compile time: it needs > 96 registers and spills 144 bytes at this CTA size, so the second TMEM read stays.)
+template <typename T, int D, int POLY4, int VAR = 0>
 __global__ void __launch_bounds__(ATT3_THREADS, 1)
 attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
   using H16 = Half16<T>;
@@ -1195,7 +1199,10 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         mx_half = fmaxf(mx0, mx1);
       }
       *my_x = mx_half;
-      named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible
+      if constexpr (VAR == 1)
+        named_bar_sync(1 + w * 4 + quarter, 64);   // just the two warps that share these 32 rows
+      else
+        named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible
       const float mx = fmaxf(mx_half, *peer_x) * sl2;
       const float m_new = fmaxf(m_run, mx);
       const bool need = (m_new - m_run) > 8.0f;   // identical in both halves (same inputs)
@@ -1250,7 +1257,10 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     mbar_wait(&o_full[w], 0);
     tc_fence_after();
     *my_x = l_run;
-    named_bar_sync(1 + w, 256);
+    if constexpr (VAR == 1)
+      named_bar_sync(1 + w * 4 + quarter, 64);
+    else
+      named_bar_sync(1 + w, 256);
     const float inv_l = 1.0f / (l_run + *peer_x);
     const int s_idx = q0 + w * ATT_BQ + r;
     const bool row_ok = s_idx < p.S;
@@ -1290,11 +1300,11 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 }
 
 
-template <typename T, int D, int POLY4>
+template <typename T, int D, int POLY4, int VAR = 0>
 static int launch_attention_v3p(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
   using Cfg = Att2Cfg<D>;
   constexpr int SMEM = Cfg::SMEM_BYTES + 2 * 2 * 128 * 4;   // + partial max / sum exchange
-  auto kern = attention_fwd_v3_kernel<T, D, POLY4>;
+  auto kern = attention_fwd_v3_kernel<T, D, POLY4, VAR>;
   static bool configured = false;
   if (!configured) {
     DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -1311,6 +1321,11 @@ static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttPara
     const char* e = getenv("DK_ATT_POLY");
     return e ? atoi(e) : 0;
   }();
+  static const bool var1 = [] {
+    const char* e = getenv("DK_ATTENTION_IMPL");
+    return e != nullptr && e[0] == '3' && e[1] == 'b';
+  }();
+  if (var1) return launch_attention_v3p<T, D, 0, 1>(ctx, tm, p, stream);
   if (poly <= 0) return launch_attention_v3p<T, D, 0>(ctx, tm, p, stream);
   if (poly == 1) return launch_attention_v3p<T, D, 1>(ctx, tm, p, stream);
   return launch_attention_v3p<T, D, 2>(ctx, tm, p, stream);

@@ -387,6 +387,20 @@ def check_attention_v2_kernel():
     return out
 
 
+def check_attention_v3b_kernel():
+    """v3 with pairwise 64-thread barriers between the two halves of a row (DK_ATTENTION_IMPL=3b, experimental):
+    same arithmetic as the default kernel"""
+    os.environ["DK_ATTENTION_IMPL"] = "3b"
+    _setup()
+    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att3b_d128_S128"),
+           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att3b_d128_S300"),
+           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att3b_d128_S1280"),
+           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att3b_d64_S1178"),
+           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att3b_S1")}
+    out["rescale"] = check_attention_large_scores()["err"]
+    return out
+
+
 def check_attention_large_scores():
     """rows whose running max keeps growing: exercises the lazy O rescale path."""
     _setup()
@@ -715,3 +729,8 @@ ALL_CHECKS = [
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,
 ]
+
+# kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
+# suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
+EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel]
+
