@@ -3,11 +3,16 @@
 CPU PyTorch fp32 restatement of the reference MMDiT forward (argmaxinc/DiffusionKit @ 498e5dba,
 python/src/diffusionkit/mlx/mmdit.py) for SD3 (dual-stream only) and FLUX (dual + single stream).
 
-PARITY UNPINNED: the reference executes on Apple MLX 0.17.3 (setup.py:32), which cannot be installed or run in
-this container (no wheel, no network, Metal-only), and the repository holds no golden tensors for this path
-(SURVEY.md §8c).  The restatement therefore follows the reference source line by line and the documented
-semantics of the MLX ops it calls; it is pinned only by the schedule/noise known-answer
-values derived from the reference formulas (tests/golden/schedule_kats.json).
+PARITY STATUS: the MLX path itself cannot run here (Apple MLX 0.17.3, setup.py:32: no wheel, no network, Metal-only)
+and the repository holds no golden tensors for it.  What pins this restatement:
+  * SD3 (dual-stream) forward: the reference's OWN PyTorch twin (python/src/diffusionkit/torch/mmdit.py), executed in
+    this container from /root/reference — outputs committed as tests/golden/reference_torch_mmdit.npz (generator:
+    tests/golden/make_reference_golden.py) and reproduced to 2e-4 by tests/test_reference_pin_cpu.py, with the one
+    documented difference between the twins (tanh vs erf GELU) switched by `gelu_tanh`.  Loading the synthetic
+    parameter tree into that module with strict=True also pins the parameter names/shapes.
+  * schedule / noise known-answer values derived from the reference formulas (tests/golden/schedule_kats.json).
+  * FLUX-only pieces (single-stream blocks, RoPE, QK-RMSNorm, reshape-patchify) have no runnable reference
+    implementation: PARITY UNPINNED for those; they follow the MLX source line by line.
 
 Conventions: parameters are a flat dict name -> tensor using the reference's module-tree names (SURVEY.md App. C,
 e.g. "multimodal_transformer_blocks.3.image_transformer_block.attn.q_proj.weight").  Linear weights are (out, in)
@@ -49,6 +54,10 @@ class RefMMDiTConfig:
     max_period: int = 10000
     dtype: torch.dtype = torch.float16          # config.dtype: sinusoid arithmetic dtype (quirk Q5)
     parallel_mlp_for_unified_blocks: bool = True
+    # False = the MLX path's nn.GELU() (erf, mmdit.py:421).  True = GELU(approximate="tanh"), what the reference's
+    # PyTorch twin uses (python/src/diffusionkit/torch/mmdit.py:242); only set by the test that pins this oracle
+    # against that module (tests/test_reference_pin_cpu.py).
+    gelu_tanh: bool = False
 
 
 def _r(x: torch.Tensor, dt: Optional[torch.dtype]) -> torch.Tensor:
@@ -143,6 +152,11 @@ class MMDiTRef:
         self._rope = None
 
     # ------------------------------------------------------------------ helpers
+    def _gelu(self, x):
+        if self.cfg.gelu_tanh:
+            return torch.nn.functional.gelu(x, approximate="tanh")
+        return gelu_erf(x)
+
     def W(self, name):
         return self.p[name]
 
@@ -210,12 +224,12 @@ class MMDiTRef:
         c = self.cfg
         attn_out = self._lin(o, bn + ".attn.o_proj")
         if parallel_mlp:
-            h1 = _r(gelu_erf(self._lin(m, bn + ".mlp.fc1")), self.dt)
+            h1 = _r(self._gelu(self._lin(m, bn + ".mlp.fc1")), self.dt)
             mlp_out = linear(h1, self.p[bn + ".mlp.fc2.weight"], None, self.dt)   # fc2.bias zeroed (mmdit.py:742)
             return _r(x + mods[2][:, None, :] * _r(attn_out + mlp_out, self.dt), self.dt)
         x = _r(x + attn_out * mods[2][:, None, :], self.dt)
         m2 = affine_transform(x, mods[3][:, None, :], mods[4][:, None, :], c.layer_norm_eps, self.dt)
-        h1 = _r(gelu_erf(self._lin(m2, bn + ".mlp.fc1")), self.dt)
+        h1 = _r(self._gelu(self._lin(m2, bn + ".mlp.fc1")), self.dt)
         mlp_out = self._lin(h1, bn + ".mlp.fc2")
         return _r(x + mods[5][:, None, :] * mlp_out, self.dt)
 

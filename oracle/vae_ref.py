@@ -4,7 +4,10 @@ CPU PyTorch fp32 restatement of the reference VAE decoder and encoder (python/sr
 336-401, 404-467), of decode_latents_to_image (mlx/__init__.py:581-584) and of read_image / encode_image_to_latents
 (mlx/__init__.py:536-551, 586-594).
 
-PARITY UNPINNED: MLX cannot run here and the repo holds no golden tensors for this path (see oracle/mmdit_ref.py).
+PARITY STATUS: the decoder is pinned against the reference's OWN PyTorch twin (python/src/diffusionkit/torch/vae.py),
+run in this container from /root/reference: tests/golden/reference_torch_vae_decoder.npz, reproduced to 2e-4 by
+tests/test_reference_pin_cpu.py with `gn_eps` = 1e-6 (the twin's value; the MLX path uses the 1e-5 default).  The
+encoder / img2img pieces have no runnable reference implementation: PARITY UNPINNED for those (MLX cannot run here).
 
 Parameters: flat dict with the reference's names; conv weights (O, kh, kw, I), Linear (out, in).
 """
@@ -47,6 +50,11 @@ def upsample_nearest(x, scale=2):
 
 
 class _VAEBlocksRef:
+    # GroupNorm epsilon: 1e-5 on the MLX path (mlx nn.GroupNorm default, quirk Q7).  The reference's PyTorch twin uses
+    # 1e-6 (python/src/diffusionkit/torch/vae.py:20); tests/test_reference_pin_cpu.py sets it to pin this oracle
+    # against that module.
+    gn_eps = 1e-5
+
     def __init__(self, params: Dict[str, torch.Tensor], act_dtype: Optional[torch.dtype],
                  block_out_channels, layers_per_block: int, groups: int):
         self.p = params
@@ -56,7 +64,7 @@ class _VAEBlocksRef:
         self.groups = groups
 
     def _gn(self, x, name):
-        return group_norm(x, self.p[name + ".weight"], self.p[name + ".bias"], self.groups, 1e-5, self.dt)
+        return group_norm(x, self.p[name + ".weight"], self.p[name + ".bias"], self.groups, self.gn_eps, self.dt)
 
     def _conv(self, x, name):
         return conv3x3(x, self.p[name + ".weight"], self.p[name + ".bias"], self.dt)
