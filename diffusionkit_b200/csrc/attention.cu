@@ -983,10 +983,12 @@ attention_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 constexpr int ATT3_THREADS = 576;
 
 // POLY4: of every four exponentials, how many run on the FMA pipe (ex2_poly) instead of MUFU.EX2 (0, 1 or 2)
-// VAR 1 (DK_ATTENTION_IMPL=3b, experimental, not yet measured): the two threads that share a row synchronise through a
-// 64-thread named barrier of their own (one per TMEM lane quarter and Q tile) instead of the tile-wide 256-thread one.
-// Same arithmetic in the same order as VAR 0.  (Keeping the 64 scores in registers between the two passes was tried
-// at compile time: it needs > 96 registers and spills 144 bytes at this CTA size, so the second TMEM read stays.)
+// VAR 1 (DK_ATTENTION_IMPL=3b, experimental, not yet measured): shorter non-exponential phases of the softmax leg —
+// the two threads that share a row synchronise through a 64-thread named barrier of their own (one per TMEM lane quarter
+// and Q tile) instead of the tile-wide 256-thread one, and the row max runs as four independent chains.  Same
+// arithmetic as VAR 0 (max is exact).  Tried at compile time and dropped: keeping the 64 scores in registers between
+// the two passes, or issuing the second pass's first TMEM read before the exchange — both need > 96 registers at this
+// CTA size (130-140 bytes of spills).
 template <typename T, int D, int POLY4, int VAR = 0>
 __global__ void __launch_bounds__(ATT3_THREADS, 1)
 attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
@@ -1190,13 +1192,26 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if constexpr (VAR == 1) {
+          // four independent max chains of 16 instead of two of 32 (max is exact: same result)
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+          for (int i = 0; i < 16; ++i) {
+            m4[0] = fmaxf(m4[0], __uint_as_float(sr[0][i]));
+            m4[1] = fmaxf(m4[1], __uint_as_float(sr[0][16 + i]));
+            m4[2] = fmaxf(m4[2], __uint_as_float(sr[1][i]));
+            m4[3] = fmaxf(m4[3], __uint_as_float(sr[1][16 + i]));
+          }
+          mx_half = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        } else {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            mx0 = fmaxf(mx0, __uint_as_float(sr[0][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sr[1][i]));
+          }
+          mx_half = fmaxf(mx0, mx1);
         }
-        mx_half = fmaxf(mx0, mx1);
       }
       *my_x = mx_half;
       if constexpr (VAR == 1)
