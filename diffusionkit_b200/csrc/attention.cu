@@ -989,9 +989,8 @@ constexpr int ATT3_THREADS = 576;
 // arithmetic as VAR 0 (max is exact).  Tried at compile time and dropped: keeping the 64 scores in registers between
 // the two passes, or issuing the second pass's first TMEM read before the exchange — both need > 96 registers at this
 // CTA size (130-140 bytes of spills).
-template <typename T, int D, int POLY4, int VAR = 0>
-__global__ void __launch_bounds__(ATT3_THREADS, 1)
-attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+template <typename T, int D, int POLY4, int VAR>
+__device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, const AttParams& p) {
   using H16 = Half16<T>;
   using Cfg = Att2Cfg<D>;
   constexpr int KS = Cfg::KS;
@@ -1178,6 +1177,71 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
       const int kv_valid = p.S - j * ATT_BKV - hh * 64;   // valid keys in this half (tail tile only matters)
+      if constexpr (VAR == 2) {
+        // register-resident variant (attention_fwd_v3r_kernel, 112 registers): ONE TMEM read per step — the 64 scores
+        // stay in registers from the max pass to the exponentials; pairwise barrier and 4 max chains as in VAR 1
+        uint32_t sr[2][32];
+        tmem_ld_32x32(t_s, sr[0]);
+        tmem_ld_32x32(t_s + 32, sr[1]);
+        tmem_ld_wait();
+        if (kv_valid < 64) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
+        }
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          m4[0] = fmaxf(m4[0], __uint_as_float(sr[0][i]));
+          m4[1] = fmaxf(m4[1], __uint_as_float(sr[0][16 + i]));
+          m4[2] = fmaxf(m4[2], __uint_as_float(sr[1][i]));
+          m4[3] = fmaxf(m4[3], __uint_as_float(sr[1][16 + i]));
+        }
+        const float mx_h = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        *my_x = mx_h;
+        named_bar_sync(1 + w * 4 + quarter, 64);
+        const float mx2 = fmaxf(mx_h, *peer_x) * sl2;
+        const float m_new2 = fmaxf(m_run, mx2);
+        const bool need2 = (m_new2 - m_run) > 8.0f;
+        if (__any_sync(0xffffffffu, need2)) {
+          const float alpha = ex2_approx(m_run - m_new2);
+          m_run = m_new2;
+          l_run *= alpha;
+          if (j > 0) {   // rare path: 16 columns at a time, the 64 scores stay in registers meanwhile
+#pragma unroll 1
+            for (int c = 0; c < OC / 16; ++c) {
+              uint32_t o[16];
+              tmem_ld_32x16(t_o + c * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st_32x16(t_o + c * 16, o);
+            }
+          }
+        }
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = fmaf(__uint_as_float(sr[c][2 * i]), sl2, -m_run);
+            const float x1 = fmaf(__uint_as_float(sr[c][2 * i + 1]), sl2, -m_run);
+            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+            s0 += e0;
+            s1 += e1;
+            pk[i] = H16::pack(e0, e1);
+          }
+          tmem_st_32x16(t_s + c * 16, pk);
+        }
+        l_run += s0 + s1;
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_full[w]);
+        continue;
+      }
       // pass 1: partial row max over this half's 64 scores
       float mx_half;
       {
@@ -1272,7 +1336,7 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     mbar_wait(&o_full[w], 0);
     tc_fence_after();
     *my_x = l_run;
-    if constexpr (VAR == 1)
+    if constexpr (VAR >= 1)
       named_bar_sync(1 + w * 4 + quarter, 64);
     else
       named_bar_sync(1 + w, 256);
@@ -1316,6 +1380,36 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
 
 
 template <typename T, int D, int POLY4, int VAR = 0>
+__global__ void __launch_bounds__(ATT3_THREADS, 1)
+attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+  attention_v3_body<T, D, POLY4, VAR>(tmQKV, p);
+}
+
+// VAR 2 under a register budget of 112 (576 x 112 = 64512 of the SM's 65536): __launch_bounds__(576) makes ptxas round
+// the CTA up to 640 threads and cap at 96.  DK_ATTENTION_IMPL=3r, experimental, not yet measured.
+template <typename T, int D>
+__global__ void __maxnreg__(112)
+attention_fwd_v3r_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
+  attention_v3_body<T, D, 0, 2>(tmQKV, p);
+}
+
+template <typename T, int D>
+static int launch_attention_v3r(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
+  using Cfg = Att2Cfg<D>;
+  constexpr int SMEM = Cfg::SMEM_BYTES + 2 * 2 * 128 * 4;
+  auto kern = attention_fwd_v3r_kernel<T, D>;
+  static bool configured = false;
+  if (!configured) {
+    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid(dk_ceil_div(p.S, 2 * ATT_BQ), p.heads, p.B);
+  kern<<<grid, ATT3_THREADS, SMEM, stream>>>(tm, p);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
+template <typename T, int D, int POLY4, int VAR = 0>
 static int launch_attention_v3p(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
   using Cfg = Att2Cfg<D>;
   constexpr int SMEM = Cfg::SMEM_BYTES + 2 * 2 * 128 * 4;   // + partial max / sum exchange
@@ -1341,6 +1435,11 @@ static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttPara
     return e != nullptr && e[0] == '3' && e[1] == 'b';
   }();
   if (var1) return launch_attention_v3p<T, D, 0, 1>(ctx, tm, p, stream);
+  static const bool var2 = [] {
+    const char* e = getenv("DK_ATTENTION_IMPL");
+    return e != nullptr && e[0] == '3' && e[1] == 'r';
+  }();
+  if (var2) return launch_attention_v3r<T, D>(ctx, tm, p, stream);
   if (poly <= 0) return launch_attention_v3p<T, D, 0>(ctx, tm, p, stream);
   if (poly == 1) return launch_attention_v3p<T, D, 1>(ctx, tm, p, stream);
   return launch_attention_v3p<T, D, 2>(ctx, tm, p, stream);
