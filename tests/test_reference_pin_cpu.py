@@ -78,3 +78,62 @@ def test_fixtures_are_what_the_reference_produces_today():
     gv = np.load(os.path.join(GOLD, "reference_torch_vae_decoder.npz"))
     img = mk.run_reference_vae(z)
     assert np.allclose(img.numpy(), gv["out"], atol=1e-6)
+
+
+@pytest.mark.skipif(not rs.reference_available(), reason="/root/reference is only mounted in the build container")
+def test_checkpoint_loaders_match_the_reference_loaders():
+    """SURVEY.md §8 row f1 pinned by reference code: an upstream-layout (Stability SD3 / LDM) checkpoint goes through the
+    REFERENCE's own key adjustments (torch/mmdit.py:424-497, torch/model_io.py:90-122) into the reference modules with
+    strict=True, and through diffusionkit_b200.model_io into the oracle — same outputs."""
+    from diffusionkit_b200 import model_io
+    from tests.test_model_io_cpu import _sd3_upstream, _vae_upstream
+
+    m, v, mio = rs.load_reference_module("mmdit"), rs.load_reference_module("vae"), rs.load_reference_module("model_io")
+    latent, text, pooled, timestep, z = mk.make_inputs()
+
+    # ---- SD3 MMDiT
+    cfg = mk.pin_mmdit_config()
+    params = init_params(mmdit_param_specs(cfg), seed=31, dtype=torch.float32)
+    upstream = _sd3_upstream(params, cfg)
+    for k in list(upstream):                        # a real checkpoint has a k bias; both loaders must drop it
+        if k.endswith("attn.qkv.bias"):
+            upstream[k] = upstream[k] + 0.3
+    # the reference loader's own prefix rule (torch/model_io.py:67-71): drop "model.diffusion_model", skip the VAE
+    stripped = {".".join(k.rsplit(".")[2:]): t for k, t in upstream.items()
+                if all(s not in k for s in ["encoder", "decoder"])}
+    ref_sd = m.mmdit_state_dict_adjustments(stripped)
+    rcfg = m.MMDiTConfig(depth=cfg.depth_multimodal, max_latent_resolution=cfg.max_latent_resolution,
+                         pooled_text_embed_dim=cfg.pooled_text_embed_dim,
+                         token_level_text_embed_dim=cfg.token_level_text_embed_dim)
+    net = m.MMDiT(rcfg).eval()
+    net.load_state_dict(ref_sd, strict=True)
+    with torch.no_grad():
+        (want,) = net(latent.permute(0, 3, 1, 2).contiguous(), text.permute(0, 2, 1)[:, :, None, :].contiguous(),
+                      pooled[:, :, None, None], timestep)
+    want = want.permute(0, 2, 3, 1)
+    mine = model_io.sd3_checkpoint_to_params(upstream)
+    model_io.check_against_specs(mine, mmdit_param_specs(cfg))
+    rc = ref_config(cfg)
+    rc.gelu_tanh = True
+    ref = MMDiTRef(rc, mine, act_dtype=None)
+    ref.cache_modulation_params(pooled, timestep[:1])
+    got = ref(latent, text, timestep)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4), float((got - want).abs().max())
+
+    # ---- VAE decoder
+    vcfg = mk.pin_vae_config()
+    vparams = init_params(vae_decoder_param_specs(vcfg), seed=32, dtype=torch.float32)
+    vup = _vae_upstream(vparams, prefix="first_stage_model.decoder.")
+    boc = vcfg.block_out_channels
+    vnet = v.VAEDecoder(v.VAEDecoderConfig(resolution=z.shape[1] * 8, base_channels=boc[0],
+                                           channel_multipliers=[c // boc[0] for c in boc],
+                                           num_res_blocks=vcfg.layers_per_block - 1)).eval()
+    vnet.load_state_dict(mio.vae_decoder_state_dict_adjustments(dict(vup)), strict=True)
+    with torch.no_grad():
+        vwant = vnet(z.permute(0, 3, 1, 2).contiguous()).permute(0, 2, 3, 1)
+    vmine = model_io.vae_decoder_checkpoint_to_params(vup)
+    model_io.check_against_specs(vmine, vae_decoder_param_specs(vcfg))
+    dec = VAEDecoderRef(vmine, None, vcfg.block_out_channels, vcfg.layers_per_block)
+    dec.gn_eps = 1e-6
+    vgot = dec(z)
+    assert torch.allclose(vgot, vwant, atol=2e-4, rtol=1e-4), float((vgot - vwant).abs().max())
