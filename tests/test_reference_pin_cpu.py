@@ -137,3 +137,20 @@ def test_checkpoint_loaders_match_the_reference_loaders():
     dec.gn_eps = 1e-6
     vgot = dec(z)
     assert torch.allclose(vgot, vwant, atol=2e-4, rtol=1e-4), float((vgot - vwant).abs().max())
+
+
+@pytest.mark.skipif(not rs.reference_available(), reason="/root/reference is only mounted in the build container")
+def test_psnr_metric_is_the_reference_metric():
+    """the parity metric itself (tests use oracle.sampler_ref.compute_psnr): reference diffusionkit/utils.py:70-82"""
+    import importlib.util
+
+    from oracle.sampler_ref import compute_psnr
+
+    rs.install()
+    spec = importlib.util.spec_from_file_location("_reference_utils", "/root/reference/python/src/diffusionkit/utils.py")
+    utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(utils)
+    rng = np.random.RandomState(0)
+    a = rng.randn(3, 8, 8).astype(np.float32)
+    b = a + 0.01 * rng.randn(3, 8, 8).astype(np.float32)
+    assert abs(compute_psnr(a, b) - float(utils.compute_psnr(a, b))) < 1e-3
