@@ -3,16 +3,15 @@
 CPU PyTorch fp32 restatement of the reference MMDiT forward (argmaxinc/DiffusionKit @ 498e5dba,
 python/src/diffusionkit/mlx/mmdit.py) for SD3 (dual-stream only) and FLUX (dual + single stream).
 
-PARITY STATUS: the MLX path itself cannot run here (Apple MLX 0.17.3, setup.py:32: no wheel, no network, Metal-only)
-and the repository holds no golden tensors for it.  What pins this restatement:
-  * SD3 (dual-stream) forward: the reference's OWN PyTorch twin (python/src/diffusionkit/torch/mmdit.py), executed in
-    this container from /root/reference — outputs committed as tests/golden/reference_torch_mmdit.npz (generator:
-    tests/golden/make_reference_golden.py) and reproduced to 2e-4 by tests/test_reference_pin_cpu.py, with the one
-    documented difference between the twins (tanh vs erf GELU) switched by `gelu_tanh`.  Loading the synthetic
-    parameter tree into that module with strict=True also pins the parameter names/shapes.
+PARITY STATUS: MLX 0.17.3 (setup.py:32) cannot run here (Metal-only, no wheel, no network) and the repository holds no
+golden tensors for this path, but this restatement is pinned against the reference's own source code:
+  * FLUX and SD3 forward + modulation cache: the reference's MLX source (python/src/diffusionkit/mlx/mmdit.py) imported
+    from /root/reference and executed unmodified on a torch-backed stand-in for the MLX primitives it calls
+    (tests/golden/mlx_standin.py); fixtures tests/golden/reference_mlxsrc_{flux,sd3}_mmdit.npz, reproduced to 3e-4 by
+    tests/test_reference_mlxsrc_pin_cpu.py.  Pins the wiring, not MLX's kernel numerics.
+  * SD3 forward: additionally the reference's PyTorch twin (python/src/diffusionkit/torch/mmdit.py) —
+    tests/golden/reference_torch_mmdit.npz, tests/test_reference_pin_cpu.py (tanh GELU switched by `gelu_tanh`).
   * schedule / noise known-answer values derived from the reference formulas (tests/golden/schedule_kats.json).
-  * FLUX-only pieces (single-stream blocks, RoPE, QK-RMSNorm, reshape-patchify) have no runnable reference
-    implementation: PARITY UNPINNED for those; they follow the MLX source line by line.
 
 Conventions: parameters are a flat dict name -> tensor using the reference's module-tree names (SURVEY.md App. C,
 e.g. "multimodal_transformer_blocks.3.image_transformer_block.attn.q_proj.weight").  Linear weights are (out, in)

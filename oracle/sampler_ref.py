@@ -3,9 +3,11 @@
 CPU restatement of the reference's sampler, schedules, noise, CFG + Euler loop and latent formats:
 python/src/diffusionkit/mlx/sampler.py (all) and mlx/__init__.py:253-292, 553-584, 674-788.
 
-PARITY: the schedule / noise functions are closed-form and are pinned against known-answer values derived from the
-reference formulas (tests/golden/schedule_kats.json).  The denoise loop depends on the MMDiT
-oracle and inherits its "parity unpinned" status (see oracle/mmdit_ref.py).
+PARITY STATUS: the schedule / noise functions are closed-form and pinned against known-answer values derived from the
+reference formulas (tests/golden/schedule_kats.json); the sampler classes and the whole
+denoise_latents -> sample_euler -> CFGDenoiser loop are pinned against the reference's own source (mlx/sampler.py,
+mlx/__init__.py) executed from /root/reference on the torch-backed MLX stand-in: tests/golden/
+reference_mlxsrc_sampler.json and reference_mlxsrc_{flux,sd3}_pipeline.npz, tests/test_reference_mlxsrc_pin_cpu.py.
 """
 from __future__ import annotations
 

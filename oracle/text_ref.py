@@ -4,9 +4,12 @@ CPU PyTorch fp32 restatement of the reference text encoders: CLIPTextModel (pyth
 and SD3T5Encoder (mlx/t5.py:21-243, 316-325), plus the token batching of DiffusionPipeline._tokenize / encode_text
 (mlx/__init__.py:174-251, 642-671).
 
-PARITY UNPINNED: MLX cannot run here and the repo holds no golden tensors for this path.  Where transformers' own
-CLIPTextModel / T5EncoderModel (installed here, CPU) implement the same published architecture, tests/ cross-checks this
-restatement against them on random small configs — an independent implementation, not the reference itself.
+PARITY STATUS: pinned twice.  (1) Against the reference's MLX source (mlx/clip.py, mlx/t5.py) executed from
+/root/reference on the torch-backed MLX stand-in (tests/golden/mlx_standin.py): tests/test_reference_mlxsrc_pin_cpu.py,
+live in the build container, 3e-4 / 5e-4.  (2) Against transformers' own CLIPTextModel / T5EncoderModel (installed
+here, CPU) on random small configs — an independent implementation of the same published architectures — in
+tests/test_text_cpu.py, which also runs on the GPU box.  MLX's kernel numerics themselves cannot be pinned (MLX does
+not run here).
 
 Parameters: flat dicts with the reference's module-tree names.  `dt` (optional torch dtype) rounds every op output to
 that type, mimicking the reference's 16-bit activations; dt=None computes in fp32.

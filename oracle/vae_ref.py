@@ -4,10 +4,12 @@ CPU PyTorch fp32 restatement of the reference VAE decoder and encoder (python/sr
 336-401, 404-467), of decode_latents_to_image (mlx/__init__.py:581-584) and of read_image / encode_image_to_latents
 (mlx/__init__.py:536-551, 586-594).
 
-PARITY STATUS: the decoder is pinned against the reference's OWN PyTorch twin (python/src/diffusionkit/torch/vae.py),
-run in this container from /root/reference: tests/golden/reference_torch_vae_decoder.npz, reproduced to 2e-4 by
-tests/test_reference_pin_cpu.py with `gn_eps` = 1e-6 (the twin's value; the MLX path uses the 1e-5 default).  The
-encoder / img2img pieces have no runnable reference implementation: PARITY UNPINNED for those (MLX cannot run here).
+PARITY STATUS: decoder AND encoder are pinned against the reference's MLX source (python/src/diffusionkit/mlx/vae.py)
+executed from /root/reference on the torch-backed MLX stand-in (tests/golden/mlx_standin.py):
+tests/golden/reference_mlxsrc_vae.npz, reproduced to 3e-4 by tests/test_reference_mlxsrc_pin_cpu.py; the decoder
+additionally against the reference's PyTorch twin (python/src/diffusionkit/torch/vae.py, `gn_eps` = 1e-6 there):
+tests/golden/reference_torch_vae_decoder.npz, tests/test_reference_pin_cpu.py.  MLX's own kernel numerics cannot be
+pinned here (MLX does not run in this container).
 
 Parameters: flat dict with the reference's names; conv weights (O, kh, kw, I), Linear (out, in).
 """
