@@ -150,3 +150,25 @@ def tokenize_pair(tokenizer, text: str, negative_text: Optional[str]) -> torch.T
     tokens += [list(tokenizer.tokenize(negative_text))]
     n = max(len(t) for t in tokens)
     return torch.tensor([t + [pad] * (n - len(t)) for t in tokens], dtype=torch.int64)
+
+
+def encode_text_sd3(clip_l: CLIPTextModelRef, clip_g: CLIPTextModelRef, t5: Optional["T5EncoderRef"], tokens_l, tokens_g,
+                    tokens_t5=None):
+    """DiffusionPipeline.encode_text after tokenisation (mlx/__init__.py:212-251): hidden_states[-2] of both CLIPs side by
+    side, zero-padded to 4096 channels, T5 sequence appended along the token axis; pooled outputs side by side"""
+    pl, _, hl = clip_l(tokens_l)
+    pg, _, hg = clip_g(tokens_g)
+    cond = torch.cat([hl[-2], hg[-2]], dim=-1)
+    pooled = torch.cat([pl, pg], dim=-1)
+    cond = torch.cat([cond, torch.zeros(cond.shape[0], cond.shape[1], 4096 - cond.shape[2])], dim=-1)
+    t5c = t5(tokens_t5) if t5 is not None else torch.zeros_like(cond)
+    return torch.cat([cond, t5c], dim=1), pooled
+
+
+def encode_text_flux(clip_l: CLIPTextModelRef, t5: "T5EncoderRef", tokens_l, tokens_t5, t5_max_length: int):
+    """FluxPipeline.encode_text after tokenisation (mlx/__init__.py:642-671): positive prompt only; the T5 ids are copied
+    into a zero buffer of T5_MAX_LENGTH"""
+    pooled, _, _ = clip_l(tokens_l[[0]])
+    padded = torch.zeros((1, t5_max_length), dtype=tokens_t5.dtype)
+    padded[:, : tokens_t5.shape[1]] = tokens_t5[[0]]
+    return t5(padded), pooled

@@ -313,3 +313,151 @@ def test_clip_tokenizer_matches_reference_tokenizer(tmp_path):
                  " ".join(["cat"] * 200)]:
         assert mine.tokenize(text) == ref.tokenize(text), text
     assert mine.eos_token == ref.eos_token and mine.bos_token == ref.bos_token
+
+
+class _WordTokenizer:
+    """minimal object with the interface the pipelines' _tokenize uses (tokenize / max_length / pad flags / eos_token)"""
+
+    def __init__(self, max_length, pad_with_eos, eos=99, bos=None, vocab_size=100):
+        self.max_length, self.pad_with_eos, self.pad_to_max_length = max_length, pad_with_eos, True
+        self.eos_token, self._bos, self._v = eos, bos, vocab_size
+
+    def tokenize(self, text):
+        ids = [1 + (sum(map(ord, w)) % (self._v - 3)) for w in text.split()][: self.max_length - 2]
+        return ([self._bos] if self._bos is not None else []) + ids + [self.eos_token]
+
+
+@LIVE
+def test_encode_text_composition_matches_reference_pipeline_source():
+    """the reference's own _tokenize / encode_text of both pipelines (mlx/__init__.py:174-251, 642-671) on the stand-in, vs
+    the product's host-side _tokenize and the oracle's encode_text_* composition"""
+    import sys
+
+    from transformers import T5Config
+
+    from diffusionkit_b200.config import CLIPTextModelConfig, T5EncoderConfig
+    from diffusionkit_b200.pipeline import DiffusionPipeline as OurPipe
+    from diffusionkit_b200.text_encoders import clip_param_specs, t5_param_specs
+    from oracle.text_ref import CLIPTextModelRef, T5EncoderRef, encode_text_flux, encode_text_sd3, tokenize_pair
+
+    dm = mk.load_reference_pipeline_package()
+    mx = sys.modules["mlx.core"]
+    from diffusionkit.mlx import clip as rclip, config as rcfg, t5 as rt5
+
+    cl = CLIPTextModelConfig(num_layers=2, model_dims=128, num_heads=2, vocab_size=100, projection_dim=None)
+    cg = CLIPTextModelConfig(num_layers=2, model_dims=192, num_heads=3, vocab_size=100, projection_dim=192, hidden_act="gelu")
+    tc = T5EncoderConfig(vocab_size=100, d_model=4096, d_kv=64, d_ff=128, num_layers=1, num_heads=2)
+    pl = init_params(clip_param_specs(cl), seed=91, dtype=torch.float32)
+    pg = init_params(clip_param_specs(cg), seed=92, dtype=torch.float32)
+    pt = init_params(t5_param_specs(tc), seed=93, dtype=torch.float32)
+    pt["wte.weight"] *= 30.0
+
+    def ref_clip(c, p):
+        m = rclip.CLIPTextModel(rcfg.CLIPTextModelConfig(num_layers=c.num_layers, model_dims=c.model_dims,
+                                                         num_heads=c.num_heads, max_length=c.max_length,
+                                                         vocab_size=c.vocab_size, projection_dim=c.projection_dim,
+                                                         hidden_act=c.hidden_act))
+        m.load_weights(mk.to_mx(p), strict=True)
+        return m
+
+    t5 = rt5.SD3T5Encoder(T5Config(vocab_size=tc.vocab_size, d_model=tc.d_model, d_kv=tc.d_kv, d_ff=tc.d_ff,
+                                   num_layers=tc.num_layers, num_heads=tc.num_heads, feed_forward_proj="gated-gelu",
+                                   relative_attention_num_buckets=32, relative_attention_max_distance=128,
+                                   layer_norm_epsilon=1e-6), low_memory_mode=False)
+    t5.load_weights(mk.to_mx(pt), strict=True)
+    tok_l, tok_g = _WordTokenizer(77, True, bos=98), _WordTokenizer(77, False, bos=98)
+    text, neg = "a photo of an astronaut riding a horse on mars", "blurry low quality"
+    o_l = CLIPTextModelRef(pl, cl.num_layers, cl.num_heads, cl.hidden_act)
+    o_g = CLIPTextModelRef(pg, cg.num_layers, cg.num_heads, cg.hidden_act)
+    o_t = T5EncoderRef(pt, tc.num_layers, tc.num_heads)
+
+    for kind in ("sd3", "flux"):
+        Pipe = dm.DiffusionPipeline if kind == "sd3" else dm.FluxPipeline
+        pipe = object.__new__(Pipe)
+        pipe.clip_l, pipe.clip_g, pipe.t5_encoder = ref_clip(cl, pl), ref_clip(cg, pg), t5
+        pipe.tokenizer_l, pipe.tokenizer_g = tok_l, tok_g
+        t5_len = 64 if kind == "sd3" else 48
+        pipe.t5_tokenizer = _WordTokenizer(t5_len, False, eos=1)
+        pipe.use_t5 = True
+        pipe.model_version = "pin"
+        dm.T5_MAX_LENGTH["pin"] = t5_len
+        for cfgw in (5.0, 0.0):
+            # token batching: reference _tokenize == product _tokenize == oracle tokenize_pair
+            n = neg if cfgw > 1 else None
+            for tk in (tok_l, tok_g, pipe.t5_tokenizer):
+                want_tok = torch.tensor(pipe._tokenize(tk, text, n).tolist())
+                assert torch.equal(OurPipe._tokenize(None, tk, text, n), want_tok)
+                assert torch.equal(tokenize_pair(tk, text, n), want_tok)
+            cond, pooled = pipe.encode_text(text, cfgw, neg)
+            tl, tg, tt = [tokenize_pair(tk, text, n) for tk in (tok_l, tok_g, pipe.t5_tokenizer)]
+            if kind == "sd3":
+                got_c, got_p = encode_text_sd3(o_l, o_g, o_t, tl, tg, tt)
+                assert cond.shape == (2, 77 + t5_len, 4096) and pooled.shape == (2, 128 + 192)
+            else:
+                got_c, got_p = encode_text_flux(o_l, o_t, tl, tt, t5_len)
+                assert cond.shape == (1, t5_len, 4096) and pooled.shape == (1, 128)
+            assert torch.allclose(got_c, cond.t, atol=5e-4, rtol=1e-4), (kind, cfgw)
+            assert torch.allclose(got_p, pooled.t, atol=5e-4, rtol=1e-4), (kind, cfgw)
+
+
+@LIVE
+def test_img2img_flow_matches_reference_pipeline_source(tmp_path):
+    """image_path / denoise arguments (mlx/__init__.py:270-285, 536-551, 586-594): read_image incl. the LANCZOS resize to
+    multiples of 64, VAE encoder, clipped-logvar posterior sample drawn with the SAME seeded noise as the diffusion
+    noise, process_in, schedule trimming, noise_scaling with a tensor x_T — reference source on the stand-in vs the
+    oracle composition the GPU check (tests/model_checks.py::check_pipeline_img2img) compares the product against"""
+    import sys
+
+    from PIL import Image
+
+    from diffusionkit_b200.config import VAEEncoderConfig
+    from diffusionkit_b200.pipeline import DiffusionPipeline as OurPipe
+    from oracle.vae_ref import encode_image_to_latents, read_image_array
+
+    dm = mk.load_reference_pipeline_package()
+    mx = sys.modules["mlx.core"]
+    from diffusionkit.mlx import config as rcfg_mod, mmdit as rmm, vae as rvae
+
+    flux, _ = mk.pin_configs()
+    params = init_params(mmdit_param_specs(flux), seed=mk.SEEDS["flux"], dtype=torch.float32)
+    ecfg = VAEEncoderConfig(block_out_channels=(32, 64, 64, 64), layers_per_block=2)
+    eparams = init_params(vae_encoder_param_specs(ecfg), seed=mk.SEEDS["vae_enc"], dtype=torch.float32)
+    pipe = object.__new__(dm.FluxPipeline)
+    pipe.mmdit = rmm.MMDiT(mk.reference_config(rcfg_mod, flux))
+    pipe.mmdit.load_weights(mk.to_mx(params), strict=True)
+    pipe.encoder = rvae.VAEEncoder(in_channels=3, out_channels=32, block_out_channels=list(ecfg.block_out_channels),
+                                   layers_per_block=ecfg.layers_per_block, resnet_groups=32)
+    pipe.encoder.load_weights(mk.to_mx(eparams), strict=True)
+    pipe.sampler, pipe.latent_format = dm.FluxSampler(shift=1.0), dm.FluxLatentFormat()
+    pipe.activation_dtype = pipe.dtype = pipe.float16_dtype = mx.float32
+    pipe.load_mmdit = lambda only_modulation_dict=False: [(k, mx.array(v.clone())) for k, v in params.items()
+                                                          if "adaLN" in k]
+    rng = np.random.RandomState(3)
+    img = (rng.rand(100, 150, 3) * 255).astype(np.uint8)            # not a multiple of 64: resized to 64 x 128
+    path = str(tmp_path / "in.png")
+    Image.fromarray(img).save(path)
+    cond, pooled = mk.make_pipeline_inputs("flux")
+    steps, denoise, seed = 4, 0.5, 9
+    latent, iter_time = pipe.denoise_latents(mx.array(cond.clone()), mx.array(pooled.clone()), num_steps=steps,
+                                             cfg_weight=0.0, latent_size=(2, 2), seed=seed, image_path=path,
+                                             denoise=denoise)
+    assert len(iter_time) == steps - int(steps * (1 - denoise)) and latent.shape == (1, 8, 16, 16)
+
+    # product host side: the same pixels after the resize rule
+    ours_u8 = OurPipe._load_image_u8(None, path)
+    ref_img = pipe.read_image(path).t
+    assert ours_u8.shape == (64, 128, 3)
+    assert torch.allclose(read_image_array(torch.from_numpy(ours_u8)), ref_img, atol=1e-6)
+
+    # oracle composition
+    enc = VAEEncoderRef(eparams, None, ecfg.block_out_channels, ecfg.layers_per_block)
+    sampler = sr.FluxSamplerRef(1.0)
+    sig = sr.get_sigmas(sampler, steps)[int(steps * (1 - denoise)):]
+    noise = sr.get_noise(seed, 8, 16)
+    z = encode_image_to_latents(enc, read_image_array(torch.from_numpy(ours_u8)), noise)
+    x_T = (z - 0.1159) * 0.3611
+    ref = MMDiTRef(ref_config(flux), params, act_dtype=None)
+    x = sr.sample_euler(lambda xin, c, t: ref(xin, c, t), ref.cache_modulation_params,
+                        sampler.noise_scaling(float(sig[0]), noise, x_T), sig, cond, pooled, 0.0, torch.float32)
+    got = sr.process_out(x, "flux")
+    assert torch.allclose(got, latent.t, atol=2e-3, rtol=1e-3), float((got - latent.t).abs().max())
