@@ -110,6 +110,26 @@ def run_reference_vae(latent, image):
     return dec(mx.array(latent.clone())).t.clone(), enc(mx.array(image.clone())).t.clone(), dcfg, ecfg
 
 
+def run_reference_vae_fullwidth(latent, image_u8):
+    """the reference VAE decoder / encoder at their REAL widths (128, 256, 512, 512) — the product's tensor-core convs
+    need Cin % 64 == 0, so the GPU checks compare against these — on a small image; read_image's scaling included"""
+    mx = sys.modules.get("mlx.core") or (mlx_standin.install() or sys.modules["mlx.core"])
+    rvae = load_reference_mlx("vae")
+    dcfg, ecfg = VAEDecoderConfig(), VAEEncoderConfig()
+    dec = rvae.VAEDecoder(in_channels=16, out_channels=3, block_out_channels=list(dcfg.block_out_channels),
+                          layers_per_block=dcfg.layers_per_block, resnet_groups=32)
+    dec.load_weights(to_mx(init_params(vae_decoder_param_specs(dcfg), seed=SEEDS["vae_dec"], dtype=torch.float32)),
+                     strict=True)
+    enc = rvae.VAEEncoder(in_channels=3, out_channels=32, block_out_channels=list(ecfg.block_out_channels),
+                          layers_per_block=ecfg.layers_per_block, resnet_groups=32)
+    enc.load_weights(to_mx(init_params(vae_encoder_param_specs(ecfg), seed=SEEDS["vae_enc"], dtype=torch.float32)),
+                     strict=True)
+    img = (mx.array(image_u8.clone())[:, :, :3].astype(mx.float32) / 255) * 2 - 1.0      # mlx/__init__.py:548-549
+    decoded = dec(mx.array(latent.clone()))
+    decoded_image = mx.clip(decoded / 2 + 0.5, 0, 1)                                       # :581-584
+    return decoded.t.clone(), decoded_image.t.clone(), enc(mx.expand_dims(img, axis=0)).t.clone()
+
+
 def run_reference_sampler():
     mx = sys.modules["mlx.core"]
     rs = load_reference_mlx("sampler")
@@ -223,6 +243,13 @@ if __name__ == "__main__":
     print("vae", tuple(d.shape), tuple(e.shape))
     with open(os.path.join(HERE, "reference_mlxsrc_sampler.json"), "w") as f:
         json.dump(run_reference_sampler(), f, indent=1)
+    zf = torch.randn((1, 8, 8, 16), generator=torch.Generator().manual_seed(54))
+    img_u8 = torch.from_numpy(np.random.RandomState(55).randint(0, 256, (64, 64, 3)).astype(np.uint8))
+    draw, dimg, ehid = run_reference_vae_fullwidth(zf, img_u8)
+    np.savez_compressed(os.path.join(HERE, "reference_mlxsrc_vae_fullwidth.npz"), latent=zf.numpy(),
+                        image_u8=img_u8.numpy(), decoded=draw.numpy().astype(np.float16),
+                        decoded_image=dimg.numpy().astype(np.float16), encoded=ehid.numpy())
+    print("vae full width", tuple(draw.shape), tuple(ehid.shape))
     for kind, (steps, cfgw, shift, lat, seed, _) in PIPELINE_CASES.items():
         cond, pooled = make_pipeline_inputs(kind)
         latent, image, sig, n_iter = run_reference_pipeline(kind, cond, pooled, steps, cfgw, shift, lat, seed)

@@ -561,6 +561,56 @@ def check_full_size_text_encoders():
     return out
 
 
+def check_product_vs_reference_source():
+    """The CUDA product directly against outputs of the REFERENCE'S OWN SOURCE — its MLX files executed (fp32) on the
+    torch-backed stand-in for the MLX primitives, tests/golden/make_reference_mlx_golden.py — with no oracle in between:
+    FLUX and SD3 MMDiT forward through the modulation cache, VAE decoder (raw output and clipped image) and VAE encoder
+    (uint8 image in, read_image scaling fused) at their real widths.  16-bit product vs fp32 reference source, so the
+    bounds are the 16-bit-vs-fp32 ones of this file with some headroom (this comparison has no 16-bit emulation on the
+    reference side); the measured values are returned."""
+    from tests.golden import make_reference_mlx_golden as mk
+
+    out = {}
+    flux, sd3 = mk.pin_configs()
+    for kind, cfg, dtype in (("flux", flux, torch.bfloat16), ("sd3", sd3, torch.float16)):
+        g = np.load(os.path.join(GOLD, f"reference_mlxsrc_{kind}_mmdit.npz"))
+        latent, text, pooled, timesteps = [torch.from_numpy(g[k]) for k in ("latent", "text", "pooled", "timesteps")]
+        ti = int(g["t_index"])
+        p16 = {k: v.to(dtype) for k, v in init_params(mmdit_param_specs(cfg), seed=mk.SEEDS[kind],
+                                                       dtype=torch.float32).items()}
+        m = dk.MMDiT(cfg, {k: v.to(DEV) for k, v in p16.items()})
+        m.cache_modulation_params(pooled.to(dtype).to(DEV), [float(t) for t in timesteps])
+        got = m(latent_image_embeddings=latent.to(dtype).to(DEV),
+                token_level_text_embeddings=text.to(dtype).to(DEV).unsqueeze(2),
+                timestep=torch.full((latent.shape[0],), float(timesteps[ti])))
+        torch.cuda.synchronize()
+        want = torch.from_numpy(g["out"])
+        r, ps = rel_l2(got, want), psnr(want, got)
+        assert r <= 3e-2 and ps >= 30.0, f"{kind} vs reference source: rel_l2={r:.3e} psnr={ps:.1f}"
+        out[kind + "_rel_l2"], out[kind + "_psnr"] = r, ps
+    g = np.load(os.path.join(GOLD, "reference_mlxsrc_vae_fullwidth.npz"))
+    dt = torch.bfloat16
+    # same CPU-generated fp32 weights as the fixture, rounded to 16 bits, then moved (a CUDA generator would differ)
+    dec = dk.VAEDecoder({k: v.to(dt).to(DEV) for k, v in init_params(
+        vae_decoder_param_specs(VAEDecoderConfig()), seed=mk.SEEDS["vae_dec"], dtype=torch.float32).items()})
+    raw = dec(torch.from_numpy(g["latent"]).to(dt).to(DEV))
+    want_raw = torch.from_numpy(g["decoded"].astype(np.float32))
+    out["vae_decoder_rel_l2"] = rel_l2(raw, want_raw)
+    assert out["vae_decoder_rel_l2"] <= 6e-2, out
+    Bo, Ho, Wo, _ = raw.shape
+    padded = raw.as_strided((Bo, Ho, Wo, raw.stride(2)), (raw.stride(0), raw.stride(1), raw.stride(2), 1))
+    f, _ = ops.image_post(padded)
+    out["vae_image_psnr"] = psnr(torch.from_numpy(g["decoded_image"].astype(np.float32)), f)
+    assert out["vae_image_psnr"] >= 28.0, out
+    enc = dk.VAEEncoder({k: v.to(dt).to(DEV) for k, v in init_params(
+        vae_encoder_param_specs(VAEEncoderConfig()), seed=mk.SEEDS["vae_enc"], dtype=torch.float32).items()})
+    hid = enc(torch.from_numpy(g["image_u8"]).unsqueeze(0).to(DEV))
+    torch.cuda.synchronize()
+    out["vae_encoder_rel_l2"] = rel_l2(hid, torch.from_numpy(g["encoded"]))
+    assert out["vae_encoder_rel_l2"] <= 4e-2, out
+    return out
+
+
 def check_full_size_sd35_properties():
     """SD3.5-large at its real width/depth (SD3_8b: 38 blocks, 38 heads x 64, hidden 2432, QK-norm; 8 B synthetic
     parameters), 512x512, CFG: determinism, batch independence, finiteness."""
@@ -621,7 +671,7 @@ def check_full_size_vae_properties():
     return {"u8_max_diff_batch_vs_solo": int(d.max()), "mean": float(f2.mean())}
 
 
-ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_mmdit_sd35_tiny, check_pipeline_q4_ckpt,
+ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_product_vs_reference_source, check_mmdit_sd35_tiny, check_pipeline_q4_ckpt,
               check_full_size_sd35_properties, check_clip_tiny, check_t5_tiny, check_pipeline_encode_text,
               check_full_size_text_encoders, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
               check_vae_decode_tiny, check_vae_decode_batch_fp16, check_vae_encode_tiny, check_vae_encode_batch_fp16,

@@ -461,3 +461,22 @@ def test_img2img_flow_matches_reference_pipeline_source(tmp_path):
                         sampler.noise_scaling(float(sig[0]), noise, x_T), sig, cond, pooled, 0.0, torch.float32)
     got = sr.process_out(x, "flux")
     assert torch.allclose(got, latent.t, atol=2e-3, rtol=1e-3), float((got - latent.t).abs().max())
+
+
+def test_oracle_fullwidth_vae_matches_reference_mlx_source():
+    """the real-width decoder / encoder fixture the GPU check compares the product against, reproduced by the oracle"""
+    from diffusionkit_b200.config import VAEDecoderConfig, VAEEncoderConfig
+    from oracle.vae_ref import decode_latents_to_image, read_image_array
+
+    g = np.load(os.path.join(GOLD, "reference_mlxsrc_vae_fullwidth.npz"))
+    dcfg, ecfg = VAEDecoderConfig(), VAEEncoderConfig()
+    dec = VAEDecoderRef(init_params(vae_decoder_param_specs(dcfg), seed=mk.SEEDS["vae_dec"], dtype=torch.float32), None,
+                        dcfg.block_out_channels, dcfg.layers_per_block)
+    z = torch.from_numpy(g["latent"])
+    assert torch.allclose(dec(z), torch.from_numpy(g["decoded"].astype(np.float32)), atol=2e-2, rtol=2e-3)   # fp16 store
+    assert torch.allclose(decode_latents_to_image(dec, z), torch.from_numpy(g["decoded_image"].astype(np.float32)),
+                          atol=2e-3)
+    enc = VAEEncoderRef(init_params(vae_encoder_param_specs(ecfg), seed=mk.SEEDS["vae_enc"], dtype=torch.float32), None,
+                        ecfg.block_out_channels, ecfg.layers_per_block)
+    e = enc(read_image_array(torch.from_numpy(g["image_u8"])))
+    assert torch.allclose(e, torch.from_numpy(g["encoded"]), atol=5e-4, rtol=1e-4)
