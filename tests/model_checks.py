@@ -565,9 +565,9 @@ def check_product_vs_reference_source():
     """The CUDA product directly against outputs of the REFERENCE'S OWN SOURCE — its MLX files executed (fp32) on the
     torch-backed stand-in for the MLX primitives, tests/golden/make_reference_mlx_golden.py — with no oracle in between:
     FLUX and SD3 MMDiT forward through the modulation cache, VAE decoder (raw output and clipped image) and VAE encoder
-    (uint8 image in, read_image scaling fused) at their real widths.  16-bit product vs fp32 reference source, so the
-    bounds are the 16-bit-vs-fp32 ones of this file with some headroom (this comparison has no 16-bit emulation on the
-    reference side); the measured values are returned."""
+    (uint8 image in, read_image scaling fused) at their real widths.  16-bit product vs fp32 reference source; bounds =
+    the 16-bit-vs-fp32 tolerances of this file.  Measured on B200: FLUX rel-L2 8.1e-3 / 54.3 dB, SD3 9.1e-4 / 73.5 dB,
+    decoder 1.5e-2 (image 47.1 dB), encoder 1.4e-2."""
     from tests.golden import make_reference_mlx_golden as mk
 
     out = {}
@@ -586,7 +586,7 @@ def check_product_vs_reference_source():
         torch.cuda.synchronize()
         want = torch.from_numpy(g["out"])
         r, ps = rel_l2(got, want), psnr(want, got)
-        assert r <= 3e-2 and ps >= 30.0, f"{kind} vs reference source: rel_l2={r:.3e} psnr={ps:.1f}"
+        assert r <= 2e-2 and ps >= 35.0, f"{kind} vs reference source: rel_l2={r:.3e} psnr={ps:.1f}"
         out[kind + "_rel_l2"], out[kind + "_psnr"] = r, ps
     g = np.load(os.path.join(GOLD, "reference_mlxsrc_vae_fullwidth.npz"))
     dt = torch.bfloat16
@@ -596,18 +596,18 @@ def check_product_vs_reference_source():
     raw = dec(torch.from_numpy(g["latent"]).to(dt).to(DEV))
     want_raw = torch.from_numpy(g["decoded"].astype(np.float32))
     out["vae_decoder_rel_l2"] = rel_l2(raw, want_raw)
-    assert out["vae_decoder_rel_l2"] <= 6e-2, out
+    assert out["vae_decoder_rel_l2"] <= 3e-2, out
     Bo, Ho, Wo, _ = raw.shape
     padded = raw.as_strided((Bo, Ho, Wo, raw.stride(2)), (raw.stride(0), raw.stride(1), raw.stride(2), 1))
     f, _ = ops.image_post(padded)
     out["vae_image_psnr"] = psnr(torch.from_numpy(g["decoded_image"].astype(np.float32)), f)
-    assert out["vae_image_psnr"] >= 28.0, out
+    assert out["vae_image_psnr"] >= 35.0, out
     enc = dk.VAEEncoder({k: v.to(dt).to(DEV) for k, v in init_params(
         vae_encoder_param_specs(VAEEncoderConfig()), seed=mk.SEEDS["vae_enc"], dtype=torch.float32).items()})
     hid = enc(torch.from_numpy(g["image_u8"]).unsqueeze(0).to(DEV))
     torch.cuda.synchronize()
     out["vae_encoder_rel_l2"] = rel_l2(hid, torch.from_numpy(g["encoded"]))
-    assert out["vae_encoder_rel_l2"] <= 4e-2, out
+    assert out["vae_encoder_rel_l2"] <= 3e-2, out
     return out
 
 
