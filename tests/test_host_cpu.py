@@ -231,3 +231,30 @@ def test_read_image_resize_rule(tmp_path):
         DiffusionPipeline._load_image_u8(None, arr[:40, :40])
     with pytest.raises(ValueError):
         DiffusionPipeline._load_image_u8(None, arr[:64, :64, 0])
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/dkb200.h is the FFI contract: it has to compile as C99 and as C++ on its own, and a C program that only
+    includes it must link against the shared library"""
+    import shutil
+
+    hdr = os.path.join(ROOT, "include", "dkb200.h")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-x", "c++", hdr])
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "dkb200.h"\n'
+                   'int main(void) { dk_ctx* c = NULL; int rc = dk_ctx_create(0, &c);\n'
+                   '  printf("%s|%d|%s\\n", dk_version(), rc, rc ? dk_last_error() : "");\n'
+                   '  if (c) dk_ctx_destroy(c); return 0; }\n')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-ldkb200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, out.stdout + out.stderr
+    if not torch.cuda.is_available():
+        assert "|0|" not in out.stdout          # no device here: create fails with a message instead of crashing
