@@ -1,0 +1,45 @@
+// Shared definitions of the attention kernels (attention.cu: the current kernel; attention_legacy.cu: the earlier
+// generations kept selectable for same-box A/B measurements).
+#pragma once
+
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace dk {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 128;
+
+struct AttParams {
+  int B, S, heads, split;
+  float scale_log2;  // scale * log2(e)
+  int debug;         // timing experiments only (DK_ATT_DEBUG): 1 = skip the exponentials, 2 = also skip the max pass
+  void* out0;
+  long long ld0;
+  void* out1;
+  long long ld1;
+};
+
+// two 128-row Q tiles per CTA, K / V rings shared by both (v2, v2a, v3)
+template <int D>
+struct Att2Cfg {
+  static constexpr int KS = (D == 128) ? 2 : 4;      // K / V ring depth
+  static constexpr int TILE_BYTES = 128 * D * 2;
+  static constexpr int OFF_Q = 0;                    // Q_A, Q_B
+  static constexpr int OFF_K = 2 * TILE_BYTES;
+  static constexpr int OFF_V = OFF_K + KS * TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_V + KS * TILE_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int TMEM_S = 0;     // + 128 * w
+  static constexpr int TMEM_O = 256;   // + 128 * w
+};
+
+}  // namespace dk
+
+// Older kernels (attention_legacy.cu).  impl: 1 = one Q tile per CTA, P through shared memory; 2 = two Q tiles, one
+// softmax warpgroup each, P in TMEM; 3 ("2a") = the first version of 2.
+int dk_launch_attention_legacy(dk_ctx* ctx, int impl, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
+                               cudaStream_t stream);

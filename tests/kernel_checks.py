@@ -366,7 +366,7 @@ def check_attention_d64():
 
 
 def check_attention_v1_kernel():
-    """the single-Q-tile kernel with P staged through shared memory (DK_ATTENTION_V1=1) stays correct"""
+    """the single-Q-tile kernel with P staged through shared memory (DK_ATTENTION_IMPL=1) stays correct"""
     os.environ["DK_ATTENTION_IMPL"] = "1"
     _setup()
     return {"d128": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att_v1_d128"),
