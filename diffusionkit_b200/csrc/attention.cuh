@@ -43,3 +43,8 @@ struct Att2Cfg {
 // softmax warpgroup each, P in TMEM; 3 ("2a") = the first version of 2.
 int dk_launch_attention_legacy(dk_ctx* ctx, int impl, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
                                cudaStream_t stream);
+
+// EXPERIMENTAL one-Q-tile kernel with a double-buffered score accumulator (attention_v4.cu, DK_ATTENTION_IMPL=4)
+int dk_launch_attention_v4(dk_ctx* ctx, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
+                           cudaStream_t stream);
+

@@ -414,6 +414,22 @@ def check_attention_v3r_kernel():
     return out
 
 
+def check_attention_v4_kernel():
+    """one Q tile per CTA, double-buffered scores, two alternating softmax sets (DK_ATTENTION_IMPL=4, experimental):
+    odd / even numbers of K/V tiles, a single tile, tails, both head dims, split outputs, the lazy-rescale path"""
+    os.environ["DK_ATTENTION_IMPL"] = "4"
+    _setup()
+    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att4_d128_S128"),
+           "d128_S256": _attention_case(1, 256, 2, 128, torch.bfloat16, name="att4_d128_S256"),
+           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att4_d128_S300"),
+           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att4_d128_S1280"),
+           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att4_d64_S1178"),
+           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att4_d64_S333"),
+           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att4_S1")}
+    out["rescale"] = check_attention_large_scores()["err"]
+    return out
+
+
 def check_attention_large_scores():
     """rows whose running max keeps growing: exercises the lazy O rescale path."""
     _setup()
@@ -745,5 +761,5 @@ ALL_CHECKS = [
 
 # kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
 # suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
-EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel]
+EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel]
 
