@@ -199,7 +199,12 @@ print("OK", rank, mine)
 def test_gloo_world2_weight_broadcast_and_sharding(tmp_path):
     script = tmp_path / "w.py"
     script.write_text(_GLOO_WORKER)
-    env = dict(os.environ, DK_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT="29731", WORLD_SIZE="2")
+    import socket
+
+    with socket.socket() as sock:                      # a free port: a fixed one can still be in TIME_WAIT from the last run
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    env = dict(os.environ, DK_ROOT=ROOT, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=180)[0] for p in procs]
