@@ -17,8 +17,8 @@
 //                                consumed by PV(j-1): tcgen05.mma of one thread executes in issue order)
 //   TMEM: S0 [0,128)  S1 [128,256)  O [256,256+D);  P(j) aliases the first half of each 64-column half of S[j&1].
 //
-// Running max: one value per row in shared memory (m_row).  The set of step j reads the value published by the set of
-// step j-1 (mbarrier m_ready), raises it lazily (only when the tile max exceeds it by more than 2^8), publishes it
+// Running max: per row in shared memory, one slot per set (m_row[set]).  The set of step j reads the slot published by
+// the set of step j-1 (mbarrier m_ready), raises it lazily (only when the tile max exceeds it by more than 2^8), publishes it
 // BEFORE its exponentials so the next set is not held up, and — in the rare raise — rescales O after PV(j-1) has
 // retired (mbarrier pv_done) and before it lets PV(j) start (p_full).  Row sums stay per thread, tagged with the max
 // they were accumulated against, and are brought to the final max once at the end (4 partials per row).
@@ -36,8 +36,8 @@ struct Att4Cfg {
   static constexpr int OFF_K = TILE_BYTES;
   static constexpr int OFF_V = OFF_K + KS * TILE_BYTES;
   static constexpr int OFF_BAR = OFF_V + KS * TILE_BYTES;
-  static constexpr int OFF_XCH = OFF_BAR + 512;      // float xmax[2][2][128], m_row[128], lpart[4][128]
-  static constexpr int XCH_BYTES = (4 * 128 + 128 + 4 * 128) * 4;
+  static constexpr int OFF_XCH = OFF_BAR + 512;      // float xmax[2][2][128], m_row[2][128], lpart[4][128]
+  static constexpr int XCH_BYTES = (4 * 128 + 2 * 128 + 4 * 128) * 4;
   static constexpr int SMEM_BYTES = OFF_XCH + XCH_BYTES + 1024;
   static constexpr int TMEM_COLS = 512;
   static constexpr int TMEM_S = 0;     // + 128 * (step & 1)
@@ -66,11 +66,15 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   uint64_t* s_full = v_empty + KS;         // [2]  QK(j) retired into S[j&1]
   uint64_t* p_full = s_full + 2;           // [2]  set j&1 published P(j)                         (256 arrivals)
   uint64_t* m_ready = p_full + 2;          // [2]  set j&1 published the running max after step j (256 arrivals)
-  uint64_t* pv_done = m_ready + 2;         // [1]  PV(j) retired (one phase per step)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* pv_done = m_ready + 2;         // [1]  PV(j) retired (one phase per step; only waited on by the step-j+1 set)
+  uint64_t* o_full = pv_done + 1;          // [1]  the LAST PV retired (single phase: a parity wait on pv_done would be
+                                           //      ambiguous for a set that finished its steps two or more phases ago)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
   float* xmax = reinterpret_cast<float*>(smem + Cfg::OFF_XCH);   // [set 2][half 2][row 128]
-  float* m_row = xmax + 4 * 128;                                  // [row 128]
-  float* lpart = m_row + 128;                                     // [set 2][half 2][row 128]
+  float* m_row = xmax + 4 * 128;                                  // [set 2][row 128]: slot s is written by set s only —
+                                                                  // with one slot the slower half of a set could read the
+                                                                  // value its own twin has just published for this step
+  float* lpart = m_row + 2 * 128;                                 // [set 2][half 2][row 128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -96,6 +100,7 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       mbar_init(&m_ready[i], 256);
     }
     mbar_init(pv_done, 1);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 17) {
@@ -162,7 +167,7 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       umma_commit(&s_full[buf]);
       umma_commit(&k_empty[st]);
     };
-    auto issue_pv = [&](int buf, int st, bool first) {
+    auto issue_pv = [&](int buf, int st, bool first, bool last) {
       const uint32_t v_lo = v_lo0 + st * TILE16;
       const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + buf * 128;
       const uint32_t d_tmem = tmem_base + Cfg::TMEM_O;
@@ -172,6 +177,7 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
                 idesc_pv, (!first || k != 0) ? 1u : 0u);
       umma_commit(&v_empty[st]);
       umma_commit(pv_done);
+      if (last) umma_commit(o_full);
     };
     mbar_wait(q_full, 0);
     mbar_wait(&k_full[0], 0);
@@ -193,7 +199,7 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       mbar_wait(&v_full[st], par);
       mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
-      if (elect_one_sync()) issue_pv(j & 1, st, j == 0);
+      if (elect_one_sync()) issue_pv(j & 1, st, j == 0, j + 1 == n_tiles);
       __syncwarp();
       st = st_n;
       par = par_n;
@@ -251,7 +257,7 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       float m_prev = -INFINITY;
       if (j > 0) {
         mbar_wait(&m_ready[set ^ 1], ((j - 1) >> 1) & 1);
-        m_prev = m_row[r];
+        m_prev = m_row[(set ^ 1) * 128 + r];
       }
       const float m_new = fmaxf(m_prev, m_tile);
       const bool need = (m_new - m_prev) > 8.0f;   // identical in both halves of the row (same inputs); true for j == 0
@@ -277,7 +283,7 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         }
       }
       // publish the running max before the exponentials: the next step's set only needs this value
-      if (hh == 0) m_row[r] = m_use;
+      if (hh == 0) m_row[set * 128 + r] = m_use;
       mbar_arrive(&m_ready[set]);
       // this thread's partial row sum follows the max it is scaled against
       if (m_loc != m_use) {
@@ -314,10 +320,10 @@ attention_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     }
 
     // epilogue: all 512 softmax threads.  Final running max, the four partial row sums, then O / l -> global
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    mbar_wait(o_full, 0);
     tc_fence_after();
     named_bar_sync(9, 512);                     // every m_row write (made before the writers' last exponentials) is visible
-    const float m_fin = m_row[r];
+    const float m_fin = m_row[((n_tiles - 1) & 1) * 128 + r];
     lpart[(set * 2 + hh) * 128 + r] = (m_loc == -INFINITY) ? 0.f : l_loc * ex2_approx(m_loc - m_fin);
     named_bar_sync(9, 512);
     const float inv_l = 1.0f / (lpart[r] + lpart[128 + r] + lpart[256 + r] + lpart[384 + r]);

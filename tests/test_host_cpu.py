@@ -263,3 +263,14 @@ def test_header_is_plain_c(tmp_path):
     assert out.returncode == 0 and "sm_100a" in out.stdout, out.stdout + out.stderr
     if not torch.cuda.is_available():
         assert "|0|" not in out.stdout          # no device here: create fails with a message instead of crashing
+
+
+def test_attention_v4_protocol_model():
+    """csrc/attention_v4.cu (experimental, one Q tile per CTA with a double-buffered score accumulator) has its barrier
+    protocol and arithmetic mirrored in tools/sim_attention_v4.py; under random interleavings it must neither deadlock
+    nor touch a buffer in the wrong state, and must reproduce softmax attention (this model caught two protocol bugs
+    before the kernel ever ran)"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sim_attention_v4 as sim
+
+    assert sim.main(seeds=8) < 1e-9
