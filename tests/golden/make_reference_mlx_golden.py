@@ -27,7 +27,7 @@ from diffusionkit_b200.weights import (init_params, mmdit_param_specs, vae_decod
                                        vae_encoder_param_specs)
 from tests.golden import mlx_standin, reference_shims  # noqa: E402
 
-SEEDS = {"flux": 41, "sd3": 42, "vae_dec": 43, "vae_enc": 44}
+SEEDS = {"flux": 41, "sd3": 42, "vae_dec": 43, "vae_enc": 44, "sd35": 45}
 
 
 def reference_mlx_available() -> bool:
@@ -56,6 +56,18 @@ def pin_configs():
             replace(sd3, dtype=torch.float32, float16_dtype=torch.float32))
 
 
+def pin_config(kind):
+    """kind in flux / sd3 / sd35 (SD3.5 shape: learned positional embedding + QK-RMSNorm, row f4)"""
+    from dataclasses import replace
+
+    from diffusionkit_b200.config import tiny_sd35_config
+
+    if kind == "sd35":
+        return replace(tiny_sd35_config(), dtype=torch.float32, float16_dtype=torch.float32)
+    flux, sd3 = pin_configs()
+    return flux if kind == "flux" else sd3
+
+
 def reference_config(rcfg_mod, cfg):
     mx = sys.modules["mlx.core"]
     return rcfg_mod.MMDiTConfig(
@@ -80,8 +92,7 @@ def run_reference_mmdit(kind, latent, text, pooled, timesteps, t_index):
     mx = sys.modules.get("mlx.core") or (mlx_standin.install() or sys.modules["mlx.core"])
     rcfg_mod = load_reference_mlx("config")
     rmm = load_reference_mlx("mmdit")
-    flux, sd3 = pin_configs()
-    cfg = flux if kind == "flux" else sd3
+    cfg = pin_config(kind)
     params = init_params(mmdit_param_specs(cfg), seed=SEEDS[kind], dtype=torch.float32)
     model = rmm.MMDiT(reference_config(rcfg_mod, cfg))
     model.load_weights(to_mx(params), strict=True)          # the reference module tree takes exactly our parameter names
@@ -214,10 +225,9 @@ def make_pipeline_inputs(kind):
 
 
 def make_inputs(kind):
-    flux, sd3 = pin_configs()
-    cfg = flux if kind == "flux" else sd3
-    g = torch.Generator().manual_seed(51 if kind == "flux" else 52)
-    B, H, W, T = (2, 8, 12, 10) if kind == "flux" else (2, 12, 8, 14)
+    cfg = pin_config(kind)
+    g = torch.Generator().manual_seed({"flux": 51, "sd3": 52, "sd35": 56}[kind])
+    B, H, W, T = {"flux": (2, 8, 12, 10), "sd3": (2, 12, 8, 14), "sd35": (1, 10, 6, 9)}[kind]
     latent = torch.randn((B, H, W, 16), generator=g)
     text = torch.randn((B, T, cfg.token_level_text_embed_dim), generator=g)
     pooled = torch.randn((B, cfg.pooled_text_embed_dim), generator=g)
@@ -227,7 +237,7 @@ def make_inputs(kind):
 
 if __name__ == "__main__":
     assert reference_mlx_available(), "needs /root/reference"
-    for kind in ("flux", "sd3"):
+    for kind in ("flux", "sd3", "sd35"):
         latent, text, pooled, timesteps, ti = make_inputs(kind)
         y = run_reference_mmdit(kind, latent, text, pooled, timesteps, ti)
         np.savez_compressed(os.path.join(HERE, f"reference_mlxsrc_{kind}_mmdit.npz"), latent=latent.numpy(),

@@ -28,15 +28,14 @@ LIVE = pytest.mark.skipif(not mk.reference_mlx_available(), reason="/root/refere
 
 
 def _oracle_mmdit(kind, latent, text, pooled, timesteps, ti):
-    flux, sd3 = mk.pin_configs()
-    cfg = flux if kind == "flux" else sd3
+    cfg = mk.pin_config(kind)
     params = init_params(mmdit_param_specs(cfg), seed=mk.SEEDS[kind], dtype=torch.float32)
     ref = MMDiTRef(ref_config(cfg), params, act_dtype=None)
     ref.cache_modulation_params(pooled, timesteps)
     return ref(latent, text, timesteps[ti].repeat(latent.shape[0]))
 
 
-@pytest.mark.parametrize("kind", ["flux", "sd3"])
+@pytest.mark.parametrize("kind", ["flux", "sd3", "sd35"])
 def test_oracle_mmdit_matches_reference_mlx_source(kind):
     g = np.load(os.path.join(GOLD, f"reference_mlxsrc_{kind}_mmdit.npz"))
     latent, text, pooled, timesteps = [torch.from_numpy(g[k]) for k in ("latent", "text", "pooled", "timesteps")]
@@ -82,7 +81,7 @@ def test_oracle_sampler_matches_reference_mlx_source():
 
 @LIVE
 def test_mlxsrc_fixtures_are_what_the_reference_source_produces_today():
-    for kind in ("flux", "sd3"):
+    for kind in ("flux", "sd3", "sd35"):
         latent, text, pooled, timesteps, ti = mk.make_inputs(kind)
         g = np.load(os.path.join(GOLD, f"reference_mlxsrc_{kind}_mmdit.npz"))
         y = mk.run_reference_mmdit(kind, latent, text, pooled, timesteps, ti)
