@@ -37,6 +37,8 @@ WORKLOADS = {
     "C4": ("flux", "argmaxinc/mlx-FLUX.1-schnell", 128, 4, 0.0, 1.0, 4, 256),
     "C2": ("flux", "argmaxinc/mlx-FLUX.1-schnell", 64, 4, 0.0, 1.0, 1, 256),
     "C3": ("sd3", "argmaxinc/mlx-stable-diffusion-3-medium", 128, 50, 5.0, 3.0, 4, 589),
+    # BASELINE.json configs[4]: FLUX.1-dev (loaded with the schnell config, quirk Q1), 50 steps, 8 images / 8 GPUs
+    "C5": ("flux", "argmaxinc/mlx-FLUX.1-dev", 128, 50, 0.0, 1.0, 1, 512),
     # SURVEY §8 row f4 (not a BASELINE.json config): SD3.5-large, CLI defaults 1024x1024, 50 steps, cfg 5, shift 3
     "SD35": ("sd3", "argmaxinc/mlx-stable-diffusion-3.5-large", 128, 50, 5.0, 3.0, 2, 589),
 }
