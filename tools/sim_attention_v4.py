@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-KS = 2
+KS = 2            # ring depth of the D = 128 kernel; main() also runs 4 (D = 64)
 TH = 8.0          # lazy-rescale threshold (log2 units), as in the kernel
 
 
@@ -260,16 +260,18 @@ class Sim:
 
 
 def main(seeds=40):
+    global KS
     worst, rescales = 0.0, 0
     for seed in range(seeds):
+      for KS in (2, 4):
         for S in (1, 100, 128, 129, 256, 300, 640, 1000):
             for big in (False, True):
-                sim = Sim(S, 64, seed * 131 + S, big_scores=big)
+                sim = Sim(S, 64, seed * 131 + S + KS, big_scores=big)
                 out = sim.run()
                 err = float(np.abs(out - sim.reference()).max())
                 worst = max(worst, err)
                 rescales += sim.rescales if big else 0
-                assert err < 1e-9, (seed, S, big, err)
+                assert err < 1e-9, (seed, S, big, KS, err)
     assert rescales > 0, "the O-rescale path was never taken"
     return worst
 
