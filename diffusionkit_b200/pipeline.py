@@ -5,9 +5,12 @@ the decode run entirely in the CUDA kernels of libdkb200.so.
 Differences that are deliberate (documented in DESIGN.md):
   * 16-bit only (w16 = a16 = True, what the reference CLI forces, scripts/generate_images.py:117-118);
     fp32 weights/activations raise NotImplementedError.
-  * no checkpoints exist in this sandbox: weights are the deterministic synthetic initialiser of weights.py unless a
-    `params` dict (reference parameter names) is passed.  `encode_text` (CLIP/T5) raises
-    NotImplementedError; pass `conditioning` / `pooled_conditioning` to generate_image or call denoise_latents.
+  * nothing is downloaded (the reference pulls checkpoints, text encoders and vocabularies from the Hugging Face hub in
+    its constructor): weights are the deterministic synthetic initialiser of weights.py unless a `params` dict
+    (reference parameter names) or `local_ckpt=` (upstream .safetensors, model_io.py) is passed, and `encode_text` works
+    once `load_text_encoders(...)` has attached CLIP / T5 weights and tokenizers built from local files — otherwise pass
+    `conditioning` / `pooled_conditioning` to generate_image or call denoise_latents.
+  * img2img (`image_path`, `denoise`): the VAE encoder is built on first use.
   * batch-N extension: `seed` may be a list of ints — one independent image per seed (the reference is batch 1);
     a scalar seed behaves exactly like the reference.
 """
