@@ -528,7 +528,7 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
   // DK_ATT_POLY (0..2, default 0): share of the softmax exponentials evaluated on the FMA pipe (tuning knob)
   static const int legacy_impl = [] {
     const char* e = getenv("DK_ATTENTION_IMPL");
-    if (e == nullptr || e[0] == '3' || e[0] == '4') return 0;
+    if (e == nullptr || e[0] == '3' || e[0] == '4' || e[0] == '5') return 0;
     if (e[0] == '2' && e[1] == 'a') return 3;
     if (e[0] == '1') return 1;
     return 2;
@@ -538,6 +538,11 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
     return e != nullptr && e[0] == '4';
   }();
   if (use_v4) return dk_launch_attention_v4(ctx, dtype, d, tm, p, stream);   // experimental, attention_v4.cu
+  static const bool use_v5 = [] {
+    const char* e = getenv("DK_ATTENTION_IMPL");
+    return e != nullptr && e[0] == '5';
+  }();
+  if (use_v5) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
   if (legacy_impl != 0) return dk_launch_attention_legacy(ctx, legacy_impl, dtype, d, tm, p, stream);
   if (dtype == DK_BF16) {
     if (d == 128) return launch_attention_v3<__nv_bfloat16, 128>(ctx, tm, p, stream);

@@ -48,3 +48,7 @@ int dk_launch_attention_legacy(dk_ctx* ctx, int impl, int dtype, int d, const CU
 int dk_launch_attention_v4(dk_ctx* ctx, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
                            cudaStream_t stream);
 
+
+// v5 (attention_v5.cu, DK_ATTENTION_IMPL=5): persistent CTAs, register-resident scores, speculative exponentials
+int dk_launch_attention_v5(dk_ctx* ctx, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
+                           cudaStream_t stream);

@@ -311,7 +311,7 @@ extern "C" int dk_gemm(dk_ctx* ctx, const dk_gemm_args* a, void* stream_) {
   DK_REQUIRE(a->gate == nullptr || (aligned16(a->gate) && a->gate_ld % 8 == 0), "dk_gemm: gate alignment");
   DK_REQUIRE(a->res == nullptr || (aligned16(a->res) && a->ldres % 8 == 0), "dk_gemm: residual alignment");
 
-  GemmShape s;
+  GemmShape s = {};
   s.M = a->M;
   s.N = a->N;
   s.K = a->K;
@@ -420,7 +420,7 @@ static int conv3x3_impl(dk_ctx* ctx, int dtype, const void* x, const void* w, co
   g.tiles_y = dk_ceil_div(H, g.TH);
   g.cblocks = Cin / 64;
 
-  GemmShape s;
+  GemmShape s = {};
   s.M = B * H * W;
   s.N = Cout;
   s.K = 9 * Cin;

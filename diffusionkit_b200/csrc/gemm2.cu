@@ -98,7 +98,7 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // grouped rasterisation over 256-row tiles: a band of GM m-tiles is swept across all n-tiles, so W is re-read from
   // HBM once per band (M/256/GM times in total) while the band's A rows stay L2 resident
-  constexpr int GM = 16;
+  const int GM = s.gm > 0 ? s.gm : 16;
   auto decode_tile = [&](int tile, int& m_blk, int& n_blk) {
     const int group_size = GM * s.num_n;
     const int group = tile / group_size;
@@ -112,6 +112,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs), converged warp
     uint32_t stage = 0, phase = 0;
+    const int hint_a = (flags >> 4) & 3, hint_w = (flags >> 6) & 3;
+    const uint64_t pol_a = l2_policy(hint_a), pol_w = l2_policy(hint_w);
     for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       decode_tile(tile, m_blk, n_blk);
@@ -122,8 +124,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (elect_one_sync()) {
           const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
           mbar_arrive_expect_tx_cluster(full_leader, G2_A_BYTES + b_tx_bytes);
-          tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, full_leader, kb * G2_BK, a_row);
-          tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, full_leader, kb * G2_BK, b_row);
+          if (hint_a | hint_w) {
+            tma_load_2d_pair_hint(sA + stage * G2_A_BYTES, &tmA, full_leader, kb * G2_BK, a_row, pol_a);
+            tma_load_2d_pair_hint(sB + stage * G2_B_BYTES, &tmB, full_leader, kb * G2_BK, b_row, pol_w);
+          } else {
+            tma_load_2d_pair(sA + stage * G2_A_BYTES, &tmA, full_leader, kb * G2_BK, a_row);
+            tma_load_2d_pair(sB + stage * G2_B_BYTES, &tmB, full_leader, kb * G2_BK, b_row);
+          }
         }
         __syncwarp();
         if (++stage == G2_STAGES) {
@@ -286,6 +293,11 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
   s.num_m = dk_ceil_div(M, 256);
   s.num_n = dk_ceil_div(N, bn);
   s.num_k = dk_ceil_div(K, G2_BK);
+  // tuning knobs (same-box A/B): DK_GEMM_GM = m-tiles per band, DK_GEMM_HINT_A / _W = L2 policy of the operand loads
+  static const int env_gm = [] { const char* v = getenv("DK_GEMM_GM"); return v ? atoi(v) : 0; }();
+  static const int env_ha = [] { const char* v = getenv("DK_GEMM_HINT_A"); return v ? atoi(v) : 0; }();
+  static const int env_hw = [] { const char* v = getenv("DK_GEMM_HINT_W"); return v ? atoi(v) : 0; }();
+  s.gm = env_gm;
   CUtensorMap tmA, tmB;
   int dbg_flags = 0;
   {
@@ -322,7 +334,7 @@ int dk_launch_gemm_pair(dk_ctx* ctx, int dtype, const void* A, long long lda, co
     if (int rc = dk_make_tmap_16b(ctx, &tmOut, e.out, 2, dims, strides, box)) return rc;
     tma_store = tma_store_mode == 1 ? 1 : 5;   // bit 2: no cache hint
   }
-  tma_store |= dbg_flags;
+  tma_store |= dbg_flags | ((env_ha & 3) << 4) | ((env_hw & 3) << 6);
   if (dtype == DK_BF16) {
     if (bn == 256) return launch_gemm2<__nv_bfloat16, 256>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);
     if (bn == 192) return launch_gemm2<__nv_bfloat16, 192>(ctx, tmA, tmB, tmOut, tma_store, s, e, stream);

@@ -10,6 +10,7 @@ namespace dk {
 struct GemmShape {
   int M, N, K;
   int num_m, num_n, num_k;
+  int gm;   // pair kernel: m-tiles per rasterisation band (0 = default)
 };
 
 struct GemmEpi {

@@ -430,6 +430,24 @@ def check_attention_v4_kernel():
     return out
 
 
+def check_attention_v5_kernel():
+    """persistent kernel with register-resident scores and speculative exponentials (DK_ATTENTION_IMPL=5): one and many
+    work items per CTA (items > SMs), odd/even K/V tile counts, tails, both head dims, split outputs, lazy rescale"""
+    os.environ["DK_ATTENTION_IMPL"] = "5"
+    _setup()
+    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att5_d128_S128"),
+           "d128_S256": _attention_case(1, 256, 2, 128, torch.bfloat16, name="att5_d128_S256"),
+           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att5_d128_S300"),
+           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att5_d128_S1280"),
+           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att5_d64_S1178"),
+           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att5_d64_S333"),
+           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att5_S1"),
+           "many_items": _attention_case(3, 700, 24, 128, torch.bfloat16, split=100, name="att5_many"),     # 216 items
+           "many_items_d64": _attention_case(2, 1500, 24, 64, torch.float16, split=1024, name="att5_many64")}
+    out["rescale"] = check_attention_large_scores()["err"]
+    return out
+
+
 def check_attention_large_scores():
     """rows whose running max keeps growing: exercises the lazy O rescale path."""
     _setup()
@@ -748,6 +766,187 @@ def check_error_paths():
     return {"after": _gemm_case(128, 128, 64, torch.bfloat16, name="gemm_after_errors")}
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE shapes
+# Parity at the shapes bench.py times (BASELINE.json C3/C4/C5): every kernel against fp32 torch at full size, with a
+# per-block error map on top of the global rel-L2 so that ONE wrong output tile (a scheduler wrap, a TMEM phase slip,
+# a tail tile) cannot hide in the average.
+def _assert_close_blocks(name, got, ref, tol, block_tol, br=128, bc=128):
+    """global rel-L2 <= tol AND every br x bc block's rel-L2 (vs the block's own reference norm) <= block_tol"""
+    err = _assert_close(name, got, ref, tol)
+    g, r = got.reshape(-1, got.shape[-1]), ref.reshape(-1, ref.shape[-1])
+    R, Cc = g.shape
+    Rp, Cp = (R + br - 1) // br * br, (Cc + bc - 1) // bc * bc
+    worst = 0.0
+    step = max(br, (1 << 26) // max(Cp, 1) // br * br)      # ~64 M elements of fp32 scratch at a time
+    for r0 in range(0, R, step):
+        r1 = min(R, r0 + step)
+        dg = torch.zeros((((r1 - r0) + br - 1) // br * br, Cp), dtype=torch.float32, device=g.device)
+        dr = torch.zeros_like(dg)
+        dg[:r1 - r0, :Cc] = g[r0:r1].float() - r[r0:r1].float()
+        dr[:r1 - r0, :Cc] = r[r0:r1].float()
+        nb = dg.shape[0] // br
+        e = dg.reshape(nb, br, Cp // bc, bc).square().sum(dim=(1, 3)).sqrt()
+        n = dr.reshape(nb, br, Cp // bc, bc).square().sum(dim=(1, 3)).sqrt()
+        worst = max(worst, float((e / (n + 1e-20)).max()))
+        del dg, dr
+    if not worst <= block_tol:
+        raise AssertionError(f"{name}: worst {br}x{bc} block rel_l2={worst:.3e} (tol {block_tol:.1e}), global {err:.3e}")
+    return {"rel_l2": err, "worst_block": worst}
+
+
+def _ref_matmul(A, W):
+    """fp32 reference product in row chunks (the fp32 copy of a 16384 x 12288 output alone is 805 MB)"""
+    Wt = W.float().t().contiguous()
+    return torch.cat([A[i:i + 4096].float() @ Wt for i in range(0, A.shape[0], 4096)], 0)
+
+
+def check_fullsize_gemm_fc1():
+    """FLUX fc1 at the C4 bench shape: 16384 x 12288 x 3072, bias + GELU-erf (reference mlx/mmdit.py:827-835)"""
+    _setup()
+    M, N, K = 16384, 12288, 3072
+    A, W, b = _rand((M, K), torch.bfloat16), _rand((N, K), torch.bfloat16, 1 / math.sqrt(K)), _rand((N,), torch.bfloat16, 0.5)
+    ref = torch.nn.functional.gelu(_ref_matmul(A, W) + b.float())
+    got = ops.gemm(A, W, bias=b, act=ACT_GELU_ERF)
+    return _assert_close_blocks("full_fc1", got, ref, 4e-3, 1.2e-2)
+
+
+def check_fullsize_gemm_single_out():
+    """FLUX single-block output projection at the C4 shape: 17408 x 3072 x 15360 with x + gate * (.) in place
+    (reference mlx/mmdit.py:736-751; K = [attn | gelu(fc1)] = 5h)"""
+    _setup()
+    B, S, N, K = 4, 4352, 3072, 15360
+    M = B * S
+    A, W, b = _rand((M, K), torch.bfloat16), _rand((N, K), torch.bfloat16, 1 / math.sqrt(K)), _rand((N,), torch.bfloat16, 0.5)
+    x, g = _rand((M, N), torch.bfloat16), _rand((B, N), torch.bfloat16)
+    ref = x.float() + g.float().repeat_interleave(S, 0) * (_ref_matmul(A, W) + b.float())
+    got = ops.gemm(A, W, out=x, bias=b, gate=g, res=x, rows_per_batch=S, out_batch_rows=S)
+    return _assert_close_blocks("full_single_out", got, ref, 4e-3, 1.2e-2)
+
+
+def _ref_qk_norm_rope(y, pos, h, heads, d, qw, kw, rope):
+    ref = y.clone()
+    for which, w in enumerate([qw, kw]):
+        t = y[:, which * h:(which + 1) * h].reshape(-1, heads, d)
+        if w is not None:
+            t = t * torch.rsqrt((t * t).mean(-1, keepdim=True) + 1e-6) * w.float()
+        if rope is not None:
+            c, sn = rope[pos][:, None, :, 0], rope[pos][:, None, :, 1]
+            x0, x1 = t[..., 0::2], t[..., 1::2]
+            t = torch.stack([x0 * c - x1 * sn, x0 * sn + x1 * c], dim=-1).reshape(-1, heads, d)
+        ref[:, which * h:(which + 1) * h] = t.reshape(-1, h)
+    return ref
+
+
+def check_fullsize_gemm_qkv_fused():
+    """FLUX image-stream QKV at the C4 shape: 4 x 4096 rows scattered behind 256 text rows of a 4 x 4352 joint buffer,
+    K = 3072 -> 9216, QK-RMSNorm + RoPE fused (reference mlx/mmdit.py:477-488,594-606,934-942)"""
+    _setup()
+    Bt, Ss, off, S, heads, d = 4, 4096, 256, 4352, 24, 128
+    h, K, dt = heads * d, 3072, torch.bfloat16
+    A, W, bias = _rand((Bt * Ss, K), dt), _rand((3 * h, K), dt, 1 / math.sqrt(K)), _rand((3 * h,), dt, 0.3)
+    qw, kw = _rand((d,), dt, 0.1) + 1.0, _rand((d,), dt, 0.1) + 1.0
+    rope = _rope_table(S, d, DEV)
+    fused = torch.zeros((Bt * S, 3 * h), dtype=dt, device=DEV)
+    ops.gemm(A, W, out=fused, bias=bias, rows_per_batch=Ss, out_batch_rows=S, out_row_off=off,
+             qk=(heads, d, qw, kw, rope, 1e-6))
+    rows = torch.cat([torch.arange(b * S + off, b * S + off + Ss) for b in range(Bt)]).to(DEV)
+    y = _ref_matmul(A, W) + bias.float()
+    pos = (torch.arange(Bt * Ss, device=DEV) % Ss) + off
+    ref = _ref_qk_norm_rope(y, pos, h, heads, d, qw, kw, rope)
+    other = torch.ones(Bt * S, dtype=torch.bool, device=DEV)
+    other[rows] = False
+    assert float(fused[other].float().abs().max()) == 0.0, "rows outside the scatter window were written"
+    return _assert_close_blocks("full_qkv_fused", fused[rows], ref, 6e-3, 1.5e-2)
+
+
+def _attention_full_case(B, S, heads, d, dtype, split, name):
+    """fp32 reference one head at a time (a 4685^2 fp32 score matrix is 88 MB)"""
+    h = heads * d
+    qkv = _rand((B * S, 3 * h), dtype)
+    o0 = torch.zeros((B * split, h), dtype=dtype, device=DEV)
+    o1 = torch.zeros((B * (S - split), h), dtype=dtype, device=DEV)
+    ops.attention(qkv, B, S, heads, d, o0, split=split, out1=o1)
+    got = torch.cat([o0.reshape(B, split, h), o1.reshape(B, S - split, h)], dim=1)
+    ref = torch.empty((B, S, h), dtype=torch.float32, device=DEV)
+    x = qkv.reshape(B, S, 3, heads, d)
+    for b in range(B):
+        for hd in range(heads):
+            q, k, v = x[b, :, 0, hd].float(), x[b, :, 1, hd].float(), x[b, :, 2, hd].float()
+            ref[b, :, hd * d:(hd + 1) * d] = torch.softmax(q @ k.t() / math.sqrt(d), dim=-1) @ v
+    return _assert_close_blocks(name, got.reshape(B * S, h), ref.reshape(B * S, h), 1e-2, 3e-2, br=128, bc=d)
+
+
+def check_fullsize_attention():
+    """joint attention at the bench sequence lengths, all 24 heads: FLUX d=128 S=4352 (C4: 17 x 256 exactly) and
+    S=4608 (C5), SD3 d=64 fp16 S=4685 (C3: ragged tail), outputs split at the text/image boundary as the model does
+    (reference mlx/mmdit.py:594-657)"""
+    _setup()
+    return {"flux_S4352": _attention_full_case(2, 4352, 24, 128, torch.bfloat16, 256, "full_att_4352"),
+            "flux_S4608": _attention_full_case(1, 4608, 24, 128, torch.bfloat16, 512, "full_att_4608"),
+            "sd3_S4685": _attention_full_case(2, 4685, 24, 64, torch.float16, 4096, "full_att_4685")}
+
+
+def _conv_full_case(B, H, W, Cin, Cout, dtype, res, name):
+    x = _rand((B, H, W, Cin), dtype)
+    w = _rand((Cout, 3, 3, Cin), dtype, 1 / math.sqrt(9 * Cin))
+    b = _rand((Cout,), dtype, 0.5)
+    r = _rand((B, H, W, Cout), dtype) if res else None
+    got = ops.conv3x3(x, w, bias=b, res=r)
+    wf = w.float().permute(0, 3, 1, 2).contiguous()
+    ref = torch.empty((B, H, W, Cout), dtype=torch.float32, device=DEV)
+    rows = max(8, (1 << 24) // (W * max(Cin, Cout)))       # reference in horizontal bands with a one-row halo
+    for b_ in range(B):
+        for y0 in range(0, H, rows):
+            y1 = min(H, y0 + rows)
+            ya, yb = max(0, y0 - 1), min(H, y1 + 1)
+            xin = x[b_, ya:yb].float().permute(2, 0, 1)[None]
+            xin = torch.nn.functional.pad(xin, (1, 1, 1 if y0 == 0 else 0, 1 if y1 == H else 0))
+            o = torch.nn.functional.conv2d(xin, wf, b.float())[0].permute(1, 2, 0)
+            ref[b_, y0:y1] = o
+    if res:
+        ref += r.float()
+    return _assert_close_blocks(name, got.reshape(-1, Cout), ref.reshape(-1, Cout), 4e-3, 1.2e-2, br=128, bc=min(128, Cout))
+
+
+def check_fullsize_conv():
+    """VAE decoder convs at the 1024^2 decode's real extents (reference mlx/vae.py:60-101,146-149):
+    1024 x 1024 x 128 -> 128 (+ skip), 512 x 512 x 256 -> 256, and the 512 -> 256 channel change at 512^2"""
+    _setup()
+    return {"1024_128": _conv_full_case(1, 1024, 1024, 128, 128, torch.bfloat16, True, "full_conv_1024"),
+            "512_256": _conv_full_case(2, 512, 512, 256, 256, torch.bfloat16, False, "full_conv_512"),
+            "512_512to256": _conv_full_case(1, 512, 512, 512, 256, torch.bfloat16, False, "full_conv_512to256")}
+
+
+def check_fullsize_groupnorm():
+    """GroupNorm(32) + SiLU at 1024 x 1024 x 128 and 512 x 512 x 256, batch 2 (reference mlx/vae.py:72-80)"""
+    _setup()
+    out = {}
+    for (B, H, W, Cc) in [(2, 1024, 1024, 128), (2, 512, 512, 256)]:
+        dt = torch.bfloat16
+        x = _rand((B, H, W, Cc), dt, 1.5) + 0.7
+        gamma, beta = _rand((Cc,), dt, 0.1) + 1.0, _rand((Cc,), dt, 0.1)
+        stats = ops.groupnorm_stats(x, 32, 1e-5)
+        mean = torch.empty((B, 32), device=DEV, dtype=torch.float64)
+        var = torch.empty((B, 32), device=DEV, dtype=torch.float64)
+        for b_ in range(B):
+            xf = x[b_].reshape(H * W, 32, Cc // 32).double()
+            mean[b_] = xf.mean(dim=(0, 2))
+            var[b_] = xf.var(dim=(0, 2), unbiased=False)
+        out[f"mean_{Cc}"] = _assert_close("full_gn_mean", stats[..., 0], mean.float(), 1e-4)
+        out[f"rstd_{Cc}"] = _assert_close("full_gn_rstd", stats[..., 1], torch.rsqrt(var + 1e-5).float(), 1e-4)
+        got = ops.groupnorm_apply(x, stats, gamma, beta, 32, True)
+        for b_ in range(B):
+            xn = (x[b_].float().reshape(H * W, 32, Cc // 32) - mean[b_].float()[None, :, None]) * \
+                torch.rsqrt(var[b_] + 1e-5).float()[None, :, None]
+            ref = torch.nn.functional.silu((xn.reshape(H * W, Cc) * gamma.float() + beta.float()).to(dt).float())
+            out[f"apply_{Cc}_{b_}"] = _assert_close("full_gn_apply", got[b_].reshape(H * W, Cc), ref, 4e-3)
+    return out
+
+
+FULLSIZE_CHECKS = [check_fullsize_gemm_fc1, check_fullsize_gemm_single_out, check_fullsize_gemm_qkv_fused,
+                   check_fullsize_attention, check_fullsize_conv, check_fullsize_groupnorm]
+
+
 ALL_CHECKS = [
     check_gemm_single_tile, check_gemm_multi_k, check_gemm_shapes, check_gemm_persistent_large, check_gemm_epilogues,
     check_gemm_fp16, check_gemm_inplace_residual, check_gemm_w_n_major, check_gemm_fused_qk_norm_rope,
@@ -757,9 +956,10 @@ ALL_CHECKS = [
     check_attention_v1_kernel, check_attention_v2_kernel,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,
-]
+] + FULLSIZE_CHECKS
 
 # kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
 # suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
-EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel]
+EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel,
+                       check_attention_v5_kernel]
 

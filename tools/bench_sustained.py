@@ -74,7 +74,7 @@ def main():
         res[name] = {"tflops": flops_seq * it / sec / 1e12, "sm_mhz_median": mhz, "power_w_median": watts, "iters": it}
         print(name, res[name], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    tag = os.environ.get("DK_GEMM_PAIR", "1") + "_tmastore" + os.environ.get("DK_GEMM_TMA_STORE", "1")
+    tag = os.environ.get("BS_TAG") or (os.environ.get("DK_GEMM_PAIR", "1") + "_tmastore" + os.environ.get("DK_GEMM_TMA_STORE", "1"))
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"bench_sustained_pair{tag}.json"), "w"), indent=1)
 
 
