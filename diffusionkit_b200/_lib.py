@@ -167,7 +167,7 @@ class Context:
 
     @property
     def stream(self) -> int:
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(self.device).cuda_stream   # the stream of THIS context's device
 
     @property
     def launches(self) -> int:

@@ -21,6 +21,12 @@ extern "C" int dk_ctx_create(int device, dk_ctx** out) {
   int ndev = 0;
   DK_CHECK_CUDA(cudaGetDeviceCount(&ndev));
   DK_REQUIRE(device >= 0 && device < ndev, "dk_ctx_create: device %d out of range (%d devices)", device, ndev);
+  int prev_device = 0;
+  DK_CHECK_CUDA(cudaGetDevice(&prev_device));
+  struct Restore {   // the caller's current device is not ours to change
+    int d;
+    ~Restore() { cudaSetDevice(d); }
+  } restore{prev_device};
   DK_CHECK_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   DK_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -109,6 +115,7 @@ extern "C" int dk_comm_unique_id(uint8_t id_host[128]) {
 
 extern "C" int dk_comm_init(dk_ctx* ctx, int rank, int world, const uint8_t id_host[128]) {
   DK_REQUIRE(ctx != nullptr, "dk_comm_init: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_REQUIRE(ctx->nccl_comm == nullptr, "dk_comm_init: communicator already initialised");
   void* lib = dk_open_nccl();
   DK_REQUIRE(lib != nullptr, "dk_comm_init: libnccl not found");
@@ -127,6 +134,7 @@ extern "C" int dk_comm_init(dk_ctx* ctx, int rank, int world, const uint8_t id_h
 
 extern "C" int dk_comm_broadcast(dk_ctx* ctx, void* ptr, size_t bytes, int root, void* stream) {
   DK_REQUIRE(ctx != nullptr && ctx->nccl_comm != nullptr, "dk_comm_broadcast: communicator not initialised");
+  DkDeviceGuard dk_guard_(ctx);
   auto bcast = reinterpret_cast<nccl_bcast_fn>(dlsym(ctx->nccl_lib, "ncclBroadcast"));
   DK_REQUIRE(bcast != nullptr, "dk_comm_broadcast: ncclBroadcast missing");
   const int rc = bcast(ptr, ptr, bytes, /*ncclInt8*/ 0, root, ctx->nccl_comm, static_cast<cudaStream_t>(stream));

@@ -492,6 +492,7 @@ using namespace dk;
 extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, int S, int heads, int d, float scale,
                                 int split, void* out0, long long ld0, void* out1, long long ld1, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_attention_fwd: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_REQUIRE(dtype == DK_BF16 || dtype == DK_FP16, "dk_attention_fwd: bad dtype %d", dtype);
   DK_REQUIRE(d == 64 || d == 128, "dk_attention_fwd: head dim %d unsupported (64 or 128)", d);
   DK_REQUIRE(B > 0 && S > 0 && heads > 0, "dk_attention_fwd: empty problem");

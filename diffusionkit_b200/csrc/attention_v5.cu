@@ -7,7 +7,7 @@
 // the tensor pipe at 56 % (QK^T -> softmax -> PV per Q tile; the leg took ~2600 of a 3650-clock period):
 //
 //   * ONE TMEM read per step: the thread's 64 scores stay in registers from the max pass to the exponentials
-//     (112 registers per thread after setmaxnreg, see ATT5_THREADS);
+//     (streamed through two 16-column register buffers, the next TMEM read in flight behind the current one);
 //   * the two threads that share a row (key halves hh = 0 / 1, in different warps of the same scheduler) no longer
 //     meet at a named barrier between the max pass and the exponentials: each publishes its partial row max as a
 //     tagged 8-byte word in shared memory and starts the exponentials of its first 32 keys SPECULATIVELY against the
@@ -24,15 +24,12 @@
 
 namespace dk {
 
-// warps 0-15 softmax (tile = warp >> 3, half = (warp >> 2) & 1), 16 TMA, 17 MMA, 18-19 idle (they complete the fifth
-// warpgroup: setmaxnreg is a warpgroup-wide instruction).  Registers: the SM's file is 4 x 16384, one quarter per
-// scheduler, and with 18+ warps every scheduler hosts five of them -> at most 96 registers per thread at launch
-// (640 x 96 = 61440).  The auxiliary warpgroup then shrinks to 32 and the four softmax warpgroups grow to 112
-// (512 x 112 + 128 x 32 = 61440, the CTA's whole pool; per scheduler 4 x 112 x 32 + 32 x 32 = 15360 <= 16384).
-// setmaxnreg must sit INSIDE the role branches: placed before them ptxas keeps the launch budget for all code.
-constexpr int ATT5_THREADS = 640;
-constexpr int ATT5_REGS_AUX = 32;
-constexpr int ATT5_REGS_SOFTMAX = 112;
+// warps 0-15 softmax (tile = warp >> 3, half = (warp >> 2) & 1), 16 TMA, 17 MMA.  Registers: the SM's file is 4 x 16384,
+// one quarter per scheduler, and with 18 warps two schedulers host five of them -> at most 96 registers per thread
+// (a 640-thread layout with setmaxnreg, 112 for the softmax warps and 32 for the other two, was measured: correct, but
+// the MMA issuer then reloads its spilled descriptors from local memory before every batch of MMAs — 794 vs 1117 TFLOP/s).
+// The softmax leg is therefore written to fit 96: scores stream through two 16-column register buffers.
+constexpr int ATT5_THREADS = 576;
 
 template <int D>
 struct Att5Cfg {
@@ -66,23 +63,6 @@ __device__ __forceinline__ float xch_get(uint32_t slot, uint32_t tag) {
     if (t != tag && clock64() - t0 > DK_WATCHDOG_CYCLES) __trap();
   } while (t != tag);
   return __uint_as_float(v);
-}
-
-// 32 scores -> 16 packed 16-bit probabilities exp2(s * sl2 - m); the two partial sums are returned, not accumulated
-template <typename H16>
-__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], float sl2, float m, uint32_t (&pk)[16], float& sum0,
-                                          float& sum1) {
-  float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float e0 = ex2_approx(fmaf(__uint_as_float(s[2 * i]), sl2, -m));
-    const float e1 = ex2_approx(fmaf(__uint_as_float(s[2 * i + 1]), sl2, -m));
-    a0 += e0;
-    a1 += e1;
-    pk[i] = H16::pack(e0, e1);
-  }
-  sum0 = a0;
-  sum1 = a1;
 }
 
 struct Att5Work {
@@ -169,8 +149,6 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 16) {
-  setmaxnreg_dec<ATT5_REGS_AUX>();
   if (warp == 16) {
     // ------------------------------------------------------------------ TMA producer (converged warp, elected issue)
     int st = 0;
@@ -303,10 +281,8 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         par = par_n;
       }
     }
-  }
   } else {
     // -------------------------------------------------------------------- softmax warps
-    setmaxnreg_inc<ATT5_REGS_SOFTMAX>();
     const int w = warp >> 3;          // Q tile
     const int hh = (warp >> 2) & 1;   // key half of every 128-key tile
     const int quarter = warp & 3;
@@ -332,42 +308,63 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         mbar_wait_warp(&s_full[w], step & 1);
         tc_fence_after();
         const int kv_valid = p.S - j * ATT_BKV - hh * 64;   // valid keys in this half (tail tile only matters)
-        float mx_half;
-        uint32_t pk0[16], pk1[16];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        {
-          uint32_t sr[2][32];
-          tmem_ld_32x32(t_s, sr[0]);
-          tmem_ld_32x32(t_s + 32, sr[1]);
-          tmem_ld_wait();
-          if (kv_valid < 64) {
-#pragma unroll
-            for (int c = 0; c < 2; ++c)
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
-          }
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        // The 64 scores stream through two 16-column register buffers (the next TMEM read is in flight while the current
+        // chunk is processed).  Each chunk: tail mask, partial row max (FMNMX3), and — SPECULATIVELY, against the running
+        // max — the exponentials; the partner's partial max is only looked at afterwards.  Speculation is wrong only
+        // when the running max is about to be raised (first step of an item, then rarely): the step is then redone
+        // from the scores, which are still in TMEM because P has not been written yet.
+        uint32_t pk[2][16];
+        float m2[2] = {-INFINITY, -INFINITY};
+        float s0 = 0.f, s1 = 0.f;
+        const bool spec = j > 0;
+        auto chunk = [&](const uint32_t (&sc)[16], int c, bool do_max, float mref) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            m4[0] = fmax3(m4[0], __uint_as_float(sr[0][2 * i]), __uint_as_float(sr[0][2 * i + 1]));
-            m4[1] = fmax3(m4[1], __uint_as_float(sr[0][16 + 2 * i]), __uint_as_float(sr[0][17 + 2 * i]));
-            m4[2] = fmax3(m4[2], __uint_as_float(sr[1][2 * i]), __uint_as_float(sr[1][2 * i + 1]));
-            m4[3] = fmax3(m4[3], __uint_as_float(sr[1][16 + 2 * i]), __uint_as_float(sr[1][17 + 2 * i]));
+            float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
+            if (kv_valid < 64) {
+              if (c * 16 + 2 * i >= kv_valid) a0 = -INFINITY;
+              if (c * 16 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
+            }
+            if (do_max) m2[i & 1] = fmax3(m2[i & 1], a0, a1);
+            const float e0 = ex2_approx(fmaf(a0, sl2, -mref));
+            const float e1 = ex2_approx(fmaf(a1, sl2, -mref));
+            s0 += e0;
+            s1 += e1;
+            pk[c >> 1][(c & 1) * 8 + i] = H16::pack(e0, e1);
           }
-          mx_half = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          xch_put(my_slot0 + (tag & 1u) * 4096u, mx_half, tag);
-          // SPECULATIVE exponentials against the running max: right unless the max is about to be raised (first step of
-          // an item, then rarely) — the partner's partial max is only looked at afterwards
-          if (j > 0) {
-            exp_chunk<H16>(sr[0], sl2, m_run, pk0, s0, s1);
-            exp_chunk<H16>(sr[1], sl2, m_run, pk1, s2, s3);
+        };
+        auto chunk_max_only = [&](const uint32_t (&sc)[16], int c) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
+            if (kv_valid < 64) {
+              if (c * 16 + 2 * i >= kv_valid) a0 = -INFINITY;
+              if (c * 16 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
+            }
+            m2[i & 1] = fmax3(m2[i & 1], a0, a1);
           }
+        };
+        {
+          uint32_t sa[16], sb[16];
+          tmem_ld_32x16(t_s, sa);
+          tmem_ld_wait();
+          tmem_ld_32x16(t_s + 16, sb);
+          if (spec) chunk(sa, 0, true, m_run); else chunk_max_only(sa, 0);
+          tmem_ld_wait();
+          tmem_ld_32x16(t_s + 32, sa);
+          if (spec) chunk(sb, 1, true, m_run); else chunk_max_only(sb, 1);
+          tmem_ld_wait();
+          tmem_ld_32x16(t_s + 48, sb);
+          if (spec) chunk(sa, 2, true, m_run); else chunk_max_only(sa, 2);
+          tmem_ld_wait();
+          if (spec) chunk(sb, 3, true, m_run); else chunk_max_only(sb, 3);
         }
+        const float mx_half = fmaxf(m2[0], m2[1]);
+        xch_put(my_slot0 + (tag & 1u) * 4096u, mx_half, tag);
         const float mx = fmaxf(mx_half, xch_get(peer_slot0 + (tag & 1u) * 4096u, tag)) * sl2;
         const float m_new = fmaxf(m_run, mx);
         const bool need = (m_new - m_run) > 8.0f;   // identical in both halves of the row (same two inputs)
-        if (__any_sync(0xffffffffu, need) || j == 0) {
+        if (__any_sync(0xffffffffu, need) || !spec) {
           const float alpha = ex2_approx(m_run - m_new);
           m_run = m_new;
           l_run *= alpha;
@@ -382,26 +379,19 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
               tmem_st_32x16(t_o + c * 16, o);
             }
           }
-          // redo the step against the raised max: the scores are still in TMEM (P has not been written yet)
+          s0 = 0.f;
+          s1 = 0.f;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t sc[32];
-            tmem_ld_32x32(t_s + c * 32, sc);
+          for (int c = 0; c < 4; ++c) {
+            uint32_t sc[16];
+            tmem_ld_32x16(t_s + c * 16, sc);
             tmem_ld_wait();
-            if (kv_valid < 64) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (c * 32 + i >= kv_valid) sc[i] = 0xff800000u;
-            }
-            if (c == 0)
-              exp_chunk<H16>(sc, sl2, m_run, pk0, s0, s1);
-            else
-              exp_chunk<H16>(sc, sl2, m_run, pk1, s2, s3);
+            chunk(sc, c, false, m_run);
           }
         }
-        tmem_st_32x16(t_s, pk0);
-        tmem_st_32x16(t_s + 16, pk1);
-        l_run += (s0 + s1) + (s2 + s3);
+        tmem_st_32x16(t_s, pk[0]);
+        tmem_st_32x16(t_s + 16, pk[1]);
+        l_run += s0 + s1;
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();

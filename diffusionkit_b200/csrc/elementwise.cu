@@ -704,6 +704,7 @@ using namespace dk;
 extern "C" int dk_ln_modulate(dk_ctx* ctx, int dtype, const void* x, void* y, const void* shift, const void* scale,
                               long long mod_ld, int rows, int rows_per_batch, int h, float eps, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_ln_modulate: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(rows > 0 && rows_per_batch > 0, "dk_ln_modulate: empty input");
   DK_REQUIRE(h % 8 == 0 && h <= 32 * 8 * LN_MAXV, "dk_ln_modulate: h=%d unsupported (multiple of 8, <= %d)", h,
@@ -734,6 +735,7 @@ extern "C" int dk_qk_norm_rope(dk_ctx* ctx, int dtype, void* qkv, int rows, int 
                                const void* q_w, const void* k_w, const void* q_w2, const void* k_w2, const float* rope,
                                float eps, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_qk_norm_rope: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(d == 64 || d == 128, "dk_qk_norm_rope: head dim %d unsupported (64 or 128)", d);
   DK_REQUIRE(rows > 0 && S > 0 && rows % S == 0, "dk_qk_norm_rope: rows %d must be a multiple of S %d", rows, S);
@@ -759,6 +761,7 @@ extern "C" int dk_qk_norm_rope(dk_ctx* ctx, int dtype, void* qkv, int rows, int 
 extern "C" int dk_silu_add(dk_ctx* ctx, int dtype, const void* y, const void* temb, void* c, int n_t, int B, int h,
                            void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_silu_add: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(h % 8 == 0, "dk_silu_add: h must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -771,6 +774,7 @@ extern "C" int dk_silu_add(dk_ctx* ctx, int dtype, const void* y, const void* te
 
 extern "C" int dk_act(dk_ctx* ctx, int dtype, const void* x, void* y, long long n, int act, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_act: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(n % 8 == 0, "dk_act: n must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -783,6 +787,7 @@ extern "C" int dk_act(dk_ctx* ctx, int dtype, const void* x, void* y, long long 
 extern "C" int dk_patchify(dk_ctx* ctx, int dtype, const void* latent, void* rows, int B, int H, int W, int C, int order,
                            void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_patchify: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(H % 2 == 0 && W % 2 == 0, "dk_patchify: latent size must be even (got %dx%d)", H, W);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -796,6 +801,7 @@ extern "C" int dk_patchify(dk_ctx* ctx, int dtype, const void* latent, void* row
 extern "C" int dk_unpatchify(dk_ctx* ctx, int dtype, const void* rows, void* latent, int B, int H, int W, int C,
                              int order, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_unpatchify: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(H % 2 == 0 && W % 2 == 0, "dk_unpatchify: latent size must be even (got %dx%d)", H, W);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -809,6 +815,7 @@ extern "C" int dk_unpatchify(dk_ctx* ctx, int dtype, const void* rows, void* lat
 extern "C" int dk_pos_embed_crop(dk_ctx* ctx, int dtype, const void* table, void* out, int max_hw, int hp, int wp, int h,
                                  void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_pos_embed_crop: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(hp <= max_hw && wp <= max_hw, "dk_pos_embed_crop: %dx%d exceeds the %d table", hp, wp, max_hw);
   DK_REQUIRE(h % 8 == 0, "dk_pos_embed_crop: h must be a multiple of 8");
@@ -823,6 +830,7 @@ extern "C" int dk_pos_embed_crop(dk_ctx* ctx, int dtype, const void* table, void
 extern "C" int dk_copy_rows(dk_ctx* ctx, int dtype, const void* src, void* dst, int B, int rows, int h, int dst_rows,
                             int dst_off, int src_rows, int src_off, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_copy_rows: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(h % 8 == 0, "dk_copy_rows: h must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -837,6 +845,7 @@ extern "C" int dk_copy_rows(dk_ctx* ctx, int dtype, const void* src, void* dst, 
 extern "C" int dk_sampler_prepare(dk_ctx* ctx, int dtype, const float* x, void* xin, long long n_per_rep, int reps,
                                   void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_sampler_prepare: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DK_DISPATCH(dtype, (sampler_prepare_kernel<T><<<grid_for(n_per_rep, 256, ctx->sm_count), 256, 0, stream>>>(
@@ -848,6 +857,7 @@ extern "C" int dk_sampler_prepare(dk_ctx* ctx, int dtype, const float* x, void* 
 extern "C" int dk_sampler_step(dk_ctx* ctx, int dtype, float* x, const void* xin, const void* out, long long n,
                                float sigma, float sigma_next, float cfg_weight, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_sampler_step: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(sigma != 0.f, "dk_sampler_step: sigma must be non-zero");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -859,6 +869,7 @@ extern "C" int dk_sampler_step(dk_ctx* ctx, int dtype, float* x, const void* xin
 
 extern "C" int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, float a, float b, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_axpb_f32: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   axpb_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(x, y, n, a, b);
   DK_LAUNCH_CHECK(ctx);
@@ -868,6 +879,7 @@ extern "C" int dk_axpb_f32(dk_ctx* ctx, const float* x, float* y, long long n, f
 extern "C" int dk_dequant_q4(dk_ctx* ctx, int dtype, const uint32_t* wq, const void* scales, const void* biases,
                              void* out, long long N, int K, int group_size, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_dequant_q4: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(N > 0 && K > 0, "dk_dequant_q4: empty weight");
   DK_REQUIRE(group_size >= 8 && group_size % 8 == 0 && K % group_size == 0,
@@ -884,6 +896,7 @@ extern "C" int dk_dequant_q4(dk_ctx* ctx, int dtype, const uint32_t* wq, const v
 extern "C" int dk_image_pre(dk_ctx* ctx, int dtype, const uint8_t* img, void* out, long long pixels, int src_channels,
                             int cpad, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_image_pre: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(src_channels >= 3, "dk_image_pre: image needs at least 3 channels (got %d)", src_channels);
   DK_REQUIRE(cpad >= 8 && cpad % 8 == 0, "dk_image_pre: cpad (%d) must be a positive multiple of 8", cpad);
@@ -897,6 +910,7 @@ extern "C" int dk_image_pre(dk_ctx* ctx, int dtype, const uint8_t* img, void* ou
 extern "C" int dk_axpby_f32(dk_ctx* ctx, const float* x, const float* y, float* out, long long n, float a, float b,
                             void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_axpby_f32: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   axpby_kernel<<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(x, y, out, n, a, b);
   DK_LAUNCH_CHECK(ctx);
@@ -906,6 +920,7 @@ extern "C" int dk_axpby_f32(dk_ctx* ctx, const float* x, const float* y, float* 
 extern "C" int dk_vae_sample_latent(dk_ctx* ctx, int dtype, const void* hidden, const float* noise, float* out,
                                     long long pixels, int C, float shift, float scale, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_vae_sample_latent: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DK_DISPATCH(dtype, (vae_sample_latent_kernel<T><<<grid_for(pixels * C, 256, ctx->sm_count), 256, 0, stream>>>(
@@ -916,6 +931,7 @@ extern "C" int dk_vae_sample_latent(dk_ctx* ctx, int dtype, const void* hidden, 
 
 extern "C" int dk_cast_f32_to_16(dk_ctx* ctx, int dtype, const float* x, void* y, long long n, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_cast_f32_to_16: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DK_DISPATCH(dtype, (cast_f32_to_16_kernel<T><<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(
@@ -925,6 +941,7 @@ extern "C" int dk_cast_f32_to_16(dk_ctx* ctx, int dtype, const float* x, void* y
 }
 extern "C" int dk_cast_16_to_f32(dk_ctx* ctx, int dtype, const void* x, float* y, long long n, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_cast_16_to_f32: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DK_DISPATCH(dtype, (cast_16_to_f32_kernel<T><<<grid_for(n, 256, ctx->sm_count), 256, 0, stream>>>(
@@ -938,6 +955,7 @@ extern "C" int dk_groupnorm_ws_floats(int B, int G) { return B * GN_MAX_CHUNKS *
 extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* stats, float* ws, int B, int HW, int C,
                                   int G, float eps, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_groupnorm_stats: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 2048, "dk_groupnorm_stats: C=%d G=%d unsupported", C, G);
   DK_REQUIRE(ws != nullptr, "dk_groupnorm_stats: workspace of dk_groupnorm_ws_floats(B, G) floats required");
@@ -956,6 +974,7 @@ extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* 
 extern "C" int dk_groupnorm_apply(dk_ctx* ctx, int dtype, const void* x, void* y, const float* stats, const void* gamma,
                                   const void* beta, int B, int HW, int C, int G, int silu, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_groupnorm_apply: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(C % 8 == 0 && C % G == 0 && C <= 2048, "dk_groupnorm_apply: C=%d G=%d unsupported", C, G);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -975,6 +994,7 @@ extern "C" int dk_groupnorm_apply(dk_ctx* ctx, int dtype, const void* x, void* y
 extern "C" int dk_upsample_nearest2x(dk_ctx* ctx, int dtype, const void* x, void* y, int B, int H, int W, int C,
                                      void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_upsample_nearest2x: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(C % 8 == 0, "dk_upsample_nearest2x: C must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -989,6 +1009,7 @@ extern "C" int dk_upsample_nearest2x(dk_ctx* ctx, int dtype, const void* x, void
 extern "C" int dk_softmax_rows(dk_ctx* ctx, int dtype, void* x, long long rows, int n, long long ld, float scale,
                                void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_softmax_rows: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(n % 8 == 0 && ld % 8 == 0, "dk_softmax_rows: n and ld must be multiples of 8");
   DK_REQUIRE(rows > 0 && rows < (1LL << 31), "dk_softmax_rows: bad row count");
@@ -1002,6 +1023,7 @@ extern "C" int dk_softmax_rows(dk_ctx* ctx, int dtype, void* x, long long rows, 
 extern "C" int dk_image_post(dk_ctx* ctx, int dtype, const void* x, int c_stride, float* img_f32, uint8_t* img_u8,
                              long long pixels, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_image_post: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DK_DISPATCH(dtype, (image_post_kernel<T><<<grid_for(pixels * 3, 256, ctx->sm_count), 256, 0, stream>>>(

@@ -301,6 +301,7 @@ static int gemm_pair_mode() {
 
 extern "C" int dk_gemm(dk_ctx* ctx, const dk_gemm_args* a, void* stream_) {
   DK_REQUIRE(ctx != nullptr && a != nullptr, "dk_gemm: null argument");
+  DkDeviceGuard dk_guard_(ctx);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DK_REQUIRE(a->dtype == DK_BF16 || a->dtype == DK_FP16, "dk_gemm: bad dtype %d", a->dtype);
   DK_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "dk_gemm: empty problem M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -392,6 +393,7 @@ extern "C" int dk_gemm(dk_ctx* ctx, const dk_gemm_args* a, void* stream_) {
 static int conv3x3_impl(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, const void* res,
                         void* out, int B, int Hin, int Win, int Cin, int Cout, int stride, cudaStream_t stream) {
   DK_REQUIRE(ctx != nullptr, "dk_conv3x3: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_REQUIRE(dtype == DK_BF16 || dtype == DK_FP16, "dk_conv3x3: bad dtype %d", dtype);
   DK_REQUIRE(B > 0 && Hin > 0 && Win > 0, "dk_conv3x3: empty input");
   DK_REQUIRE(Cin % 64 == 0, "dk_conv3x3: Cin (%d) must be a multiple of 64 (pad the channels)", Cin);

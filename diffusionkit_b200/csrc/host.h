@@ -25,6 +25,22 @@ struct dk_ctx {
 
 void dk_set_error(const char* fmt, ...);
 
+// Every entry point runs on ITS context's device whatever the calling thread's current device is (two pipelines on
+// two GPUs in one process), and leaves the thread's device as it found it.
+struct DkDeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DkDeviceGuard(const dk_ctx* c) {
+    if (c != nullptr && cudaGetDevice(&prev) == cudaSuccess && prev != c->device)
+      switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~DkDeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DkDeviceGuard(const DkDeviceGuard&) = delete;
+  DkDeviceGuard& operator=(const DkDeviceGuard&) = delete;
+};
+
 #define DK_CHECK_CUDA(expr)                                                                        \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \

@@ -317,6 +317,7 @@ using namespace dk;
 extern "C" int dk_embedding(dk_ctx* ctx, int dtype, const void* table, const int* ids, const void* pos, void* out,
                             long long n, int d, int vocab, int pos_len, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_embedding: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(n > 0 && d > 0 && d % 8 == 0, "dk_embedding: d (%d) must be a positive multiple of 8", d);
   DK_REQUIRE(vocab > 0, "dk_embedding: empty table");
@@ -332,6 +333,7 @@ extern "C" int dk_embedding(dk_ctx* ctx, int dtype, const void* table, const int
 extern "C" int dk_layernorm(dk_ctx* ctx, int dtype, const void* x, void* y, const void* weight, const void* bias,
                             int rows, int h, float eps, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_layernorm: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(rows > 0 && h > 0 && h % 8 == 0 && h <= 4096, "dk_layernorm: h (%d) must be a multiple of 8, <= 4096", h);
   DK_REQUIRE(weight != nullptr && bias != nullptr, "dk_layernorm: weight and bias are required");
@@ -357,6 +359,7 @@ extern "C" int dk_layernorm(dk_ctx* ctx, int dtype, const void* x, void* y, cons
 extern "C" int dk_rmsnorm_f32(dk_ctx* ctx, int dtype, const float* x, const void* weight, void* y, int rows, int d,
                               float eps, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_rmsnorm_f32: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(rows > 0 && d > 0 && d % 4 == 0 && d <= 4096, "dk_rmsnorm_f32: d (%d) must be a multiple of 4, <= 4096", d);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -368,6 +371,7 @@ extern "C" int dk_rmsnorm_f32(dk_ctx* ctx, int dtype, const float* x, const void
 
 extern "C" int dk_add_f32_16(dk_ctx* ctx, int dtype, float* x, const void* y, long long n, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_add_f32_16: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(n % 8 == 0, "dk_add_f32_16: n must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -379,6 +383,7 @@ extern "C" int dk_add_f32_16(dk_ctx* ctx, int dtype, float* x, const void* y, lo
 
 extern "C" int dk_glu_gelu(dk_ctx* ctx, int dtype, const void* h, void* out, long long rows, int F, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_glu_gelu: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(rows > 0 && F > 0 && F % 8 == 0, "dk_glu_gelu: F (%d) must be a positive multiple of 8", F);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -391,6 +396,7 @@ extern "C" int dk_glu_gelu(dk_ctx* ctx, int dtype, const void* h, void* out, lon
 extern "C" int dk_attention_small(dk_ctx* ctx, int dtype, const void* qkv, const void* rel_bias, void* out, int B, int S,
                                   int heads, int head_dim, float scale, int causal, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_attention_small: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
   DK_DTYPE_OK(dtype);
   DK_REQUIRE(head_dim == 64, "dk_attention_small: head dim %d unsupported (64)", head_dim);
   DK_REQUIRE(B > 0 && heads > 0 && S > 0 && S <= AS_MAX_S, "dk_attention_small: S (%d) must be in [1, %d]", S, AS_MAX_S);

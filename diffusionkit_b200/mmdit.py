@@ -21,6 +21,7 @@ from __future__ import annotations
 
 import math
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -61,15 +62,13 @@ class MMDiT:
         self._mod_all: Optional[torch.Tensor] = None
         self._mod_cur: Optional[torch.Tensor] = None
         self._mod_batch = 0
-        self._ws_key = None
-        self._ws: Dict[str, torch.Tensor] = {}
-        self._rope_key = None
-        self._rope: Optional[torch.Tensor] = None
-        self._pos_key = None
-        self._pos: Optional[torch.Tensor] = None
+        # Everything a captured forward bakes device pointers of — workspace, RoPE table, cropped positional embedding —
+        # is owned PER SHAPE KEY together with the graph that uses it, so a graph can never outlive its buffers when one
+        # model serves several resolutions / text lengths (LRU-bounded: evicting a shape drops its graph with it).
+        self._shapes: "OrderedDict[tuple, dict]" = OrderedDict()
+        self.max_cached_shapes = int(os.environ.get("DK_MAX_CACHED_SHAPES", "4"))
         # CUDA-graph replay of the (timestep-invariant) forward: one captured graph per input shape
         self.use_cuda_graphs = os.environ.get("DK_CUDA_GRAPHS", "1") != "0"
-        self._graphs: Dict[tuple, tuple] = {}
 
     # ------------------------------------------------------------------------------------------ weight packing
     def _pack(self, P: Dict[str, torch.Tensor]):
@@ -175,7 +174,8 @@ class MMDiT:
         if self._mod_cur is None or self._mod_batch != B:
             # persistent buffer: captured graphs read the current step's modulation rows from this address
             self._mod_cur = torch.empty((B, self.mod_total), dtype=self.dtype, device=self.device)
-            self._graphs = {}
+            for st in self._shapes.values():
+                st["graph"] = None
         self._mod_batch = B
         self._mod_index = {}
         for i, t in enumerate(ts):
@@ -200,10 +200,20 @@ class MMDiT:
         return self._mod_cur[:, s_off + k * self.h: s_off + (k + 1) * self.h]
 
     # ------------------------------------------------------------------------------------------ workspace
-    def _workspace(self, B: int, N: int, T: int):
-        key = (B, N, T)
-        if self._ws_key == key:
-            return self._ws
+    def _shape_state(self, key: tuple) -> dict:
+        st = self._shapes.get(key)
+        if st is None:
+            while len(self._shapes) >= max(1, self.max_cached_shapes):
+                self._shapes.popitem(last=False)            # least recently used shape: buffers AND graph go together
+            st = {"ws": None, "rope": None, "pos": None, "graph": None}
+            self._shapes[key] = st
+        else:
+            self._shapes.move_to_end(key)
+        return st
+
+    def _workspace(self, st: dict, B: int, N: int, T: int):
+        if st["ws"] is not None:
+            return st["ws"]
         h, dt, dev = self.h, self.dtype, self.device
         S = N + T
         r = self.config.mlp_ratio
@@ -223,15 +233,14 @@ class MMDiT:
             ws["u"] = buf(B * S, h)
             ws["m_u"] = buf(B * S, h)
             ws["cat"] = buf(B * S, (1 + r) * h)
-        self._ws, self._ws_key = ws, key
+        st["ws"] = ws
         return ws
 
-    def _rope_table(self, T: int, hp: int, wp: int) -> torch.Tensor:
+    def _rope_table(self, st: dict, T: int, hp: int, wp: int) -> torch.Tensor:
         """(S, d/2, 2) fp32 cos/sin; text tokens at position (0,0,0), image token (r, c) at (0, r, c)
         (reference mmdit.py:865-911).  Cached across calls like the reference (:916-932)."""
-        key = (T, hp, wp)
-        if self._rope_key == key:
-            return self._rope
+        if st["rope"] is not None:
+            return st["rope"]
         axes = self.config.rope_axes_dim
         S = T + hp * wp
         pos = torch.zeros((S, 3), dtype=torch.float32)
@@ -244,9 +253,8 @@ class MMDiT:
             parts.append(pos[:, a:a + 1] * omega[None, :])
         ang = torch.cat(parts, dim=-1)
         assert ang.shape[1] == self.d // 2, "sum(rope_axes_dim) must equal the head dim"
-        self._rope = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous().to(self.device)
-        self._rope_key = key
-        return self._rope
+        st["rope"] = torch.stack([torch.cos(ang), torch.sin(ang)], dim=-1).contiguous().to(self.device)
+        return st["rope"]
 
     # ------------------------------------------------------------------------------------------ forward
     def _qk_fused(self, s: _Stream, rope):
@@ -298,34 +306,34 @@ class MMDiT:
                 self.select_timestep(tval)
         if self._mod_cur is None or self._mod_batch != B:
             raise DkError(f"modulation cache holds batch {self._mod_batch}, forward got batch {B}")
+        state = self._shape_state((B, H, W, Cl, T))
         if not self.use_cuda_graphs:
-            return self._forward_impl(x, text, B, H, W, Cl, T)
-        key = (B, H, W, Cl, T)
-        entry = self._graphs.get(key)
+            return self._forward_impl(state, x, text, B, H, W, Cl, T)
+        entry = state["graph"]
         if entry is None:
-            sx, st = x.clone(), text.clone()
-            self._forward_impl(sx, st, B, H, W, Cl, T)            # eager warm-up: workspaces, tables, func attributes
+            sx, stx = x.clone(), text.clone()
+            self._forward_impl(state, sx, stx, B, H, W, Cl, T)    # eager warm-up: workspaces, tables, func attributes
             torch.cuda.current_stream().synchronize()
             n0 = ops.launch_count()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                so = self._forward_impl(sx, st, B, H, W, Cl, T)
-            entry = (graph, sx, st, so, ops.launch_count() - n0)
-            self._graphs[key] = entry
-        graph, sx, st, so, n_launch = entry
+                so = self._forward_impl(state, sx, stx, B, H, W, Cl, T)
+            entry = (graph, sx, stx, so, ops.launch_count() - n0)
+            state["graph"] = entry
+        graph, sx, stx, so, n_launch = entry
         sx.copy_(x)
-        st.copy_(text)
+        stx.copy_(text)
         graph.replay()
         ops.note_graph_launches(n_launch)
         return so
 
-    def _forward_impl(self, x, text, B, H, W, Cl, T):
+    def _forward_impl(self, state, x, text, B, H, W, Cl, T):
         c = self.config
         hp, wp = H // c.patch_size, W // c.patch_size
         N = hp * wp
         S = N + T
         h, heads, d = self.h, self.heads, self.d
-        ws = self._workspace(B, N, T)
+        ws = self._workspace(state, B, N, T)
         img, txt, qkv = ws["img"], ws["txt"], ws["qkv"]
 
         # ---- input adapters (mmdit.py:195-206)
@@ -335,13 +343,12 @@ class MMDiT:
             ops.gemm(ws["rows_in"], self.w_x, out=img, bias=self.b_x)
         else:
             ops.patchify(x, 1, out=ws["rows_in"])
-            if self._pos_key != (hp, wp):
-                self._pos = ops.pos_embed_crop(self.pos_table, c.max_latent_resolution, hp, wp)
-                self._pos_key = (hp, wp)
-            ops.gemm(ws["rows_in"], self.w_x, out=img, bias=self.b_x, res=self._pos, rows_per_batch=N,
+            if state["pos"] is None:
+                state["pos"] = ops.pos_embed_crop(self.pos_table, c.max_latent_resolution, hp, wp)
+            ops.gemm(ws["rows_in"], self.w_x, out=img, bias=self.b_x, res=state["pos"], rows_per_batch=N,
                      out_batch_rows=N, res_batch_rows=0)
 
-        rope = self._rope_table(T, hp, wp) if c.pos_embed_type == PositionalEncoding.PreSDPARope else None
+        rope = self._rope_table(state, T, hp, wp) if c.pos_embed_type == PositionalEncoding.PreSDPARope else None
         # joint sequence order: FLUX [text, image] (mmdit.py:594-606), SD3 [image, text] (:608-625)
         if self.is_flux:
             off_img, off_txt, split = T, 0, T

@@ -388,6 +388,11 @@ class DiffusionPipeline:
         if conditioning.dim() == 4:
             conditioning = conditioning.squeeze(2)
         reps = 2 if cfg_weight > 0 else 1
+        if B > 1 and conditioning.shape[0] == reps and pooled_conditioning.shape[0] == reps:
+            # one prompt (what encode_text returns: [positive] or [positive | negative]), several seeds: every image of
+            # the batch shares it -> [positive x B | negative x B], the layout CFGDenoiser splits (:718)
+            conditioning = conditioning.repeat_interleave(B, dim=0)
+            pooled_conditioning = pooled_conditioning.repeat_interleave(B, dim=0)
         if conditioning.shape[0] != reps * B:
             raise DkError(
                 f"conditioning has batch {conditioning.shape[0]}, expected {reps * B} "

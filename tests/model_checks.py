@@ -518,6 +518,17 @@ def check_pipeline_encode_text():
             image, log = pipe.generate_image(prompt, num_steps=2, cfg_weight=5.0 if kind == "sd3" else 0.0,
                                              negative_text=negative, latent_size=(8, 8), seed=1, verbose=False)
             assert image.size == (64, 64) and log["text_encoding"]["time"] >= 0
+            # batch-N extension with a TEXT prompt: one prompt, several seeds -> a list of images; image i equals the
+            # single-seed run with that seed (the prompt's conditioning is shared, [positive x B | negative x B])
+            many, _ = pipe.generate_image(prompt, num_steps=2, cfg_weight=5.0 if kind == "sd3" else 0.0,
+                                          negative_text=negative, latent_size=(8, 8), seed=[1, 9], verbose=False)
+            assert isinstance(many, list) and len(many) == 2
+            solo9, _ = pipe.generate_image(prompt, num_steps=2, cfg_weight=5.0 if kind == "sd3" else 0.0,
+                                           negative_text=negative, latent_size=(8, 8), seed=9, verbose=False)
+            d0 = np.abs(np.asarray(many[0]).astype(np.int32) - np.asarray(image).astype(np.int32)).max()
+            d1 = np.abs(np.asarray(many[1]).astype(np.int32) - np.asarray(solo9).astype(np.int32)).max()
+            assert d0 <= 1 and d1 <= 1, (kind, d0, d1)
+            res[kind + "_multiseed_u8_diff"] = int(max(d0, d1))
     return res
 
 
@@ -671,9 +682,88 @@ def check_full_size_vae_properties():
     return {"u8_max_diff_batch_vs_solo": int(d.max()), "mean": float(f2.mean())}
 
 
+# ------------------------------------------------------------------------------------------------ BASELINE widths
+def _fullwidth_cfg(model_version, depth_mm, depth_uni):
+    from diffusionkit_b200.config import MODEL_CONFIGS
+
+    full = MODEL_CONFIGS[model_version]
+    return full, replace(full, depth_multimodal=depth_mm, depth_unified=depth_uni, hidden_size_override=full.hidden_size)
+
+
+def check_fullwidth_flux_vs_oracle():
+    """FLUX.1-schnell at its REAL width and the C4 sequence length (h = 3072, 24 heads x 128, S = 4096 + 256, 1024^2
+    image) through a truncated depth (1 double + 1 single block) against the fp32 oracle — the shapes bench.py times
+    (reference mlx/mmdit.py:188-266, 568-751)."""
+    full, cfg = _fullwidth_cfg("argmaxinc/mlx-FLUX.1-schnell", 1, 1)
+    assert cfg.hidden_size == 3072 and cfg.head_dim == 128
+    return _mmdit_case(cfg, torch.bfloat16, 1, (128, 128), 256)
+
+
+def check_fullwidth_flux_dev_len_vs_oracle():
+    """same at the C5 text length (S = 4096 + 512), batch 2: 4608 is not a multiple of the 256-row attention work item"""
+    full, cfg = _fullwidth_cfg("argmaxinc/mlx-FLUX.1-schnell", 1, 1)
+    return _mmdit_case(cfg, torch.bfloat16, 2, (128, 64), 512)
+
+
+def check_fullwidth_sd3_vs_oracle():
+    """SD3-medium at its real width and the C3 sequence length (h = 1536, 24 heads x 64, S = 4096 + 589 (77 + 512 T5),
+    fp16) through 2 blocks (the last one skips the text post-attention path, mlx/mmdit.py:62-66)"""
+    full, cfg = _fullwidth_cfg("argmaxinc/mlx-stable-diffusion-3-medium", 2, 0)
+    assert cfg.hidden_size == 1536 and cfg.head_dim == 64
+    return _mmdit_case(cfg, torch.float16, 1, (128, 128), 589)
+
+
+def check_vae_decode_512_vs_oracle():
+    """a complete 512 x 512 decode (latent 64^2, every layer at its real width) against the fp32 oracle
+    (reference mlx/vae.py:386-401)"""
+    return _vae_case(torch.bfloat16, 1, (64, 64), 35.0)
+
+
+def check_vae_decode_1024_vs_oracle():
+    """the BASELINE decode: 1024 x 1024 (latent 128^2, mid attention over S = 16384) against the fp32 oracle"""
+    return _vae_case(torch.bfloat16, 1, (128, 128), 35.0)
+
+
+def check_mmdit_shape_switch_graphs():
+    """one model serving shapes A, B, A, C... with CUDA-graph replay == the same model launching kernel by kernel:
+    each captured graph owns its workspace / RoPE table / cropped positional embedding, including after an LRU
+    eviction (max_cached_shapes = 2 here) — the replay of A after B must not read freed buffers"""
+    out = {}
+    for name, cfg, dt in (("flux", tiny_flux_config(), torch.bfloat16), ("sd3", tiny_sd3_config(), torch.float16)):
+        p16 = init_params(mmdit_param_specs(cfg), seed=11, dtype=dt, device=DEV)
+        mg, me = dk.MMDiT(cfg, p16), dk.MMDiT(cfg, p16)
+        mg.use_cuda_graphs, me.use_cuda_graphs = True, False
+        mg.max_cached_shapes = 2
+        gen = torch.Generator().manual_seed(3)
+        pooled = torch.randn((2, cfg.pooled_text_embed_dim), generator=gen).to(dt).to(DEV)
+        for m in (mg, me):
+            m.cache_modulation_params(pooled, [752.0, 500.0])
+        shapes = {"A": ((8, 12), 16), "B": ((16, 8), 24), "C": ((12, 12), 8)}
+        worst = 0.0
+        for step, sk in enumerate("ABACABCA"):
+            (H, W), T = shapes[sk]
+            lat = torch.randn((2, H, W, 16), generator=gen).to(dt).to(DEV)
+            txt = torch.randn((2, T, cfg.token_level_text_embed_dim), generator=gen).to(dt).to(DEV)
+            tval = 752.0 if step % 2 == 0 else 500.0
+            a = mg(lat, txt, timestep=tval).clone()
+            # garbage allocations between calls: whatever a stale graph pointed at would now hold other data
+            junk = [torch.full((1 << 18,), float("nan"), dtype=dt, device=DEV) for _ in range(8)]
+            b = me(lat, txt, timestep=tval)
+            torch.cuda.synchronize()
+            del junk
+            assert bool(torch.isfinite(a.float()).all()), f"{name} step {step} ({sk}): non-finite output"
+            assert torch.equal(a, b), f"{name} step {step} (shape {sk}): graph replay != eager, rel_l2 {rel_l2(a, b):.3e}"
+            worst = max(worst, rel_l2(a, b))
+        assert len(mg._shapes) <= 2
+        out[name] = worst
+    return out
+
+
 ALL_CHECKS = [check_mmdit_flux_tiny, check_mmdit_sd3_tiny, check_product_vs_reference_source, check_mmdit_sd35_tiny, check_pipeline_q4_ckpt,
               check_full_size_sd35_properties, check_clip_tiny, check_t5_tiny, check_pipeline_encode_text,
-              check_full_size_text_encoders, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long,
+              check_full_size_text_encoders, check_mmdit_flux_ragged, check_mmdit_sd3_d64_long, check_mmdit_shape_switch_graphs,
               check_vae_decode_tiny, check_vae_decode_batch_fp16, check_vae_encode_tiny, check_vae_encode_batch_fp16,
               check_pipeline_img2img, check_pipeline_flux_tiny, check_pipeline_sd3_cfg_tiny,
-              check_pipeline_errors, check_pipeline_local_ckpt, check_full_size_flux_properties, check_full_size_vae_properties]
+              check_pipeline_errors, check_pipeline_local_ckpt, check_full_size_flux_properties, check_full_size_vae_properties,
+              check_fullwidth_flux_vs_oracle, check_fullwidth_flux_dev_len_vs_oracle, check_fullwidth_sd3_vs_oracle,
+              check_vae_decode_512_vs_oracle, check_vae_decode_1024_vs_oracle]
