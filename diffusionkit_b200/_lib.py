@@ -79,6 +79,10 @@ SIGNATURES = {
     "dk_groupnorm_apply": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "dk_conv3x3": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "dk_conv3x3_s2": (i32, [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "dk_conv_fused_supported": (i32, [i32, i32, i32, i32]),
+    "dk_conv3x3_fused": (i32, [vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp]),
+    "dk_conv_up_weights": (i32, [vp, i32, vp, vp, i32, i32, vp]),
+    "dk_groupnorm_finalize": (i32, [vp, vp, vp, i32, i32, i32, C.c_double, f32, vp]),
     "dk_upsample_nearest2x": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, vp]),
     "dk_softmax_rows": (i32, [vp, i32, vp, i64, i32, i64, f32, vp]),
     "dk_image_post": (i32, [vp, i32, vp, i32, vp, vp, i64, vp]),

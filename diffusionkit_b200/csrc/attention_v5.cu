@@ -56,29 +56,137 @@ __device__ __forceinline__ void xch_put(uint32_t slot, float v, uint32_t tag) {
 }
 // spin until the partner has published its word for `tag` (it always has, or is a few instructions away)
 __device__ __forceinline__ float xch_get(uint32_t slot, uint32_t tag) {
-  uint32_t v, t;
-  const long long t0 = clock64();
-  do {
+  uint32_t v, t, spins = 0;
+  for (;;) {
     asm volatile("ld.volatile.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v), "=r"(t) : "r"(slot) : "memory");
-    if (t != tag && clock64() - t0 > DK_WATCHDOG_CYCLES) __trap();
-  } while (t != tag);
+    if (t == tag) break;
+    if (++spins == (1u << 28)) __trap();
+  }
   return __uint_as_float(v);
+}
+
+// One 16-score chunk: [tail mask] -> [partial row max] -> [exponentials against mref -> packed P, partial sums].
+// MASK is a template flag: only the ragged LAST K/V tile of a sequence pays for the per-element compare/select
+// (ncu on v3: ISETP + FSEL of the tail mask were 26 % of all instructions issued, on every step).
+template <typename H16, bool MASK, bool DO_MAX, bool DO_EXP>
+__device__ __forceinline__ void att5_chunk(const uint32_t (&sc)[16], int c, int kv_valid, float sl2, float mref,
+                                           float (&m2)[2], uint32_t (&pk)[2][16], float& s0, float& s1) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
+    if (MASK) {
+      if (c * 16 + 2 * i >= kv_valid) a0 = -INFINITY;
+      if (c * 16 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
+    }
+    if (DO_MAX) m2[i & 1] = fmax3(m2[i & 1], a0, a1);
+    if (DO_EXP) {
+      const float e0 = ex2_approx(fmaf(a0, sl2, -mref));
+      const float e1 = ex2_approx(fmaf(a1, sl2, -mref));
+      s0 += e0;
+      s1 += e1;
+      pk[c >> 1][(c & 1) * 8 + i] = H16::pack(e0, e1);
+    }
+  }
+}
+
+// The 64 scores of this thread stream through two 16-column register buffers (the next TMEM read is in flight while the
+// current chunk is processed).
+template <typename H16, bool MASK, bool DO_EXP>
+__device__ __forceinline__ void att5_pass(uint32_t t_s, int kv_valid, float sl2, float mref, float (&m2)[2],
+                                          uint32_t (&pk)[2][16], float& s0, float& s1) {
+  uint32_t sa[16], sb[16];
+  tmem_ld_32x16(t_s, sa);
+  tmem_ld_wait();
+  tmem_ld_32x16(t_s + 16, sb);
+  att5_chunk<H16, MASK, true, DO_EXP>(sa, 0, kv_valid, sl2, mref, m2, pk, s0, s1);
+  tmem_ld_wait();
+  tmem_ld_32x16(t_s + 32, sa);
+  att5_chunk<H16, MASK, true, DO_EXP>(sb, 1, kv_valid, sl2, mref, m2, pk, s0, s1);
+  tmem_ld_wait();
+  tmem_ld_32x16(t_s + 48, sb);
+  att5_chunk<H16, MASK, true, DO_EXP>(sa, 2, kv_valid, sl2, mref, m2, pk, s0, s1);
+  tmem_ld_wait();
+  att5_chunk<H16, MASK, true, DO_EXP>(sb, 3, kv_valid, sl2, mref, m2, pk, s0, s1);
+}
+
+// One K/V step of one softmax thread: scores S (TMEM) -> probabilities P (TMEM, over the thread's own score columns),
+// running max / sum updated.
+//   1. pass over the scores: partial row max and — SPECULATIVELY, against the running max — the exponentials
+//      (mask-free: steps that need the tail mask, and the first step of a work item, do not speculate);
+//   2. publish the partial max, read the partner's (the other 64 keys of the same rows);
+//   3. lazy rescale decision (running max raised only when it grows by more than 2^8): the same function of the same
+//      two numbers in both threads of a row.  When it fires (rare), or when the step did not speculate, O and l are
+//      rescaled and the exponentials are (re)done from the scores, which are still in TMEM because P has not been
+//      written yet — this path carries the tail mask.
+//   nospec: first step of a work item (running max = -inf, O not yet written) or the ragged last K/V tile.
+template <typename H16, int OC>
+__device__ __forceinline__ void att5_step(uint32_t t_s, uint32_t t_o, bool first, bool nospec, int kv_valid, float sl2,
+                                          float& m_run, float& l_run, uint32_t my_slot, uint32_t peer_slot,
+                                          uint32_t tag) {
+  uint32_t pk[2][16];
+  float m2[2] = {-INFINITY, -INFINITY};
+  float s0 = 0.f, s1 = 0.f;
+  if (!nospec)
+    att5_pass<H16, false, true>(t_s, kv_valid, sl2, m_run, m2, pk, s0, s1);
+  else
+    att5_pass<H16, true, false>(t_s, kv_valid, sl2, m_run, m2, pk, s0, s1);
+  const float mx_half = fmaxf(m2[0], m2[1]);
+  xch_put(my_slot, mx_half, tag);
+  const float mx = fmaxf(mx_half, xch_get(peer_slot, tag)) * sl2;
+  const float m_new = fmaxf(m_run, mx);
+  const bool need = (m_new - m_run) > 8.0f;
+  if (__any_sync(0xffffffffu, need) || nospec) {
+    const float alpha = ex2_approx(m_run - m_new);   // first step: m_run = -inf -> alpha = 0, l_run = 0
+    m_run = m_new;
+    l_run *= alpha;
+    if (!first) {   // PV(j-1) has retired: QK(j), issued after it by the same thread, has
+#pragma unroll 1
+      for (int c = 0; c < OC / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld_32x16(t_o + c * 16, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x16(t_o + c * 16, o);
+      }
+    }
+    s0 = 0.f;
+    s1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t sc[16];
+      tmem_ld_32x16(t_s + c * 16, sc);
+      tmem_ld_wait();
+      att5_chunk<H16, true, false, true>(sc, c, kv_valid, sl2, m_run, m2, pk, s0, s1);
+    }
+  }
+  tmem_st_32x16(t_s, pk[0]);
+  tmem_st_32x16(t_s + 16, pk[1]);
+  l_run += s0 + s1;
 }
 
 struct Att5Work {
   int q0, head, b;
 };
 
-// Static schedule: item i of CTA c is global item c + i * gridDim.x over a list ordered (q-pair major) so that the
-// ragged last q-pair of every (batch, head) — the cheapest items — comes LAST: the tail of the schedule is then made
-// of the short items.
+// Static schedule: item i of CTA c is global item c + i * gridDim.x.  Items are ordered with the Q-tile pair varying
+// FASTEST inside a (batch, head): the ~148 items in flight then cover ~9 (batch, head) problems whose K / V (2.2 MB
+// each at S = 4352) stay L2-resident while their 17 Q-tile pairs stream past.  (Ordering by Q-tile pair first — all 96
+// (batch, head) problems in flight at once — was measured: K / V are then re-read from HBM for every item, 860 vs
+// 1125 TFLOP/s.)
 __device__ __forceinline__ bool att5_work(const AttParams& p, int n_qpairs, int it, Att5Work& w) {
   const int total = n_qpairs * p.heads * p.B;
   const int idx = blockIdx.x + it * gridDim.x;
   if (idx >= total) return false;
-  const int bh = p.heads * p.B;
-  const int qp = idx / bh;
-  const int r = idx - qp * bh;
+  int qp, r;
+  if (p.debug & 1) {   // experiment: Q-tile-pair major
+    const int bh = p.heads * p.B;
+    qp = idx / bh;
+    r = idx - qp * bh;
+  } else {
+    r = idx / n_qpairs;
+    qp = idx - r * n_qpairs;
+  }
   w.q0 = qp * (2 * ATT_BQ);
   w.head = r % p.heads;
   w.b = r / p.heads;
@@ -124,7 +232,7 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);
+      mbar_init(&p_full[i], (p.debug & 4) ? 256 : 8);
       mbar_init(&o_full[i], 1);
       mbar_init(&o_empty[i], 8);
     }
@@ -297,6 +405,7 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     const uint32_t my_slot0 = smem_u32(xch + ((w * 2 + hh) * 128 + r) * 2);
     const uint32_t peer_slot0 = smem_u32(xch + ((w * 2 + (hh ^ 1)) * 128 + r) * 2);
     const float sl2 = p.scale_log2;
+    const bool ragged = (p.S % ATT_BKV) != 0;   // only then does the last K/V tile need the per-element mask
     uint32_t step = 0;
     uint32_t tag = 0;
     Att5Work wk;
@@ -305,103 +414,26 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       float l_run = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++step) {
         ++tag;
-        mbar_wait_warp(&s_full[w], step & 1);
+        mbar_wait(&s_full[w], step & 1);
         tc_fence_after();
         const int kv_valid = p.S - j * ATT_BKV - hh * 64;   // valid keys in this half (tail tile only matters)
-        // The 64 scores stream through two 16-column register buffers (the next TMEM read is in flight while the current
-        // chunk is processed).  Each chunk: tail mask, partial row max (FMNMX3), and — SPECULATIVELY, against the running
-        // max — the exponentials; the partner's partial max is only looked at afterwards.  Speculation is wrong only
-        // when the running max is about to be raised (first step of an item, then rarely): the step is then redone
-        // from the scores, which are still in TMEM because P has not been written yet.
-        uint32_t pk[2][16];
-        float m2[2] = {-INFINITY, -INFINITY};
-        float s0 = 0.f, s1 = 0.f;
-        const bool spec = j > 0;
-        auto chunk = [&](const uint32_t (&sc)[16], int c, bool do_max, float mref) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
-            if (kv_valid < 64) {
-              if (c * 16 + 2 * i >= kv_valid) a0 = -INFINITY;
-              if (c * 16 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
-            }
-            if (do_max) m2[i & 1] = fmax3(m2[i & 1], a0, a1);
-            const float e0 = ex2_approx(fmaf(a0, sl2, -mref));
-            const float e1 = ex2_approx(fmaf(a1, sl2, -mref));
-            s0 += e0;
-            s1 += e1;
-            pk[c >> 1][(c & 1) * 8 + i] = H16::pack(e0, e1);
-          }
-        };
-        auto chunk_max_only = [&](const uint32_t (&sc)[16], int c) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
-            if (kv_valid < 64) {
-              if (c * 16 + 2 * i >= kv_valid) a0 = -INFINITY;
-              if (c * 16 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
-            }
-            m2[i & 1] = fmax3(m2[i & 1], a0, a1);
-          }
-        };
-        {
-          uint32_t sa[16], sb[16];
-          tmem_ld_32x16(t_s, sa);
-          tmem_ld_wait();
-          tmem_ld_32x16(t_s + 16, sb);
-          if (spec) chunk(sa, 0, true, m_run); else chunk_max_only(sa, 0);
-          tmem_ld_wait();
-          tmem_ld_32x16(t_s + 32, sa);
-          if (spec) chunk(sb, 1, true, m_run); else chunk_max_only(sb, 1);
-          tmem_ld_wait();
-          tmem_ld_32x16(t_s + 48, sb);
-          if (spec) chunk(sa, 2, true, m_run); else chunk_max_only(sa, 2);
-          tmem_ld_wait();
-          if (spec) chunk(sb, 3, true, m_run); else chunk_max_only(sb, 3);
-        }
-        const float mx_half = fmaxf(m2[0], m2[1]);
-        xch_put(my_slot0 + (tag & 1u) * 4096u, mx_half, tag);
-        const float mx = fmaxf(mx_half, xch_get(peer_slot0 + (tag & 1u) * 4096u, tag)) * sl2;
-        const float m_new = fmaxf(m_run, mx);
-        const bool need = (m_new - m_run) > 8.0f;   // identical in both halves of the row (same two inputs)
-        if (__any_sync(0xffffffffu, need) || !spec) {
-          const float alpha = ex2_approx(m_run - m_new);
-          m_run = m_new;
-          l_run *= alpha;
-          if (j > 0) {   // PV(j-1) has retired: QK(j), issued after it by the same thread, has
-#pragma unroll 1
-            for (int c = 0; c < OC / 16; ++c) {
-              uint32_t o[16];
-              tmem_ld_32x16(t_o + c * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x16(t_o + c * 16, o);
-            }
-          }
-          s0 = 0.f;
-          s1 = 0.f;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t sc[16];
-            tmem_ld_32x16(t_s + c * 16, sc);
-            tmem_ld_wait();
-            chunk(sc, c, false, m_run);
-          }
-        }
-        tmem_st_32x16(t_s, pk[0]);
-        tmem_st_32x16(t_s + 16, pk[1]);
-        l_run += s0 + s1;
+        const uint32_t par_off = (tag & 1u) * 4096u;
+        att5_step<H16, OC>(t_s, t_o, j == 0, j == 0 || (ragged && j == n_tiles - 1), kv_valid, sl2, m_run, l_run,
+                           my_slot0 + par_off, peer_slot0 + par_off, tag);
         tmem_st_wait();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[w]);
+        if (p.debug & 4) {
+          mbar_arrive(&p_full[w]);
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[w]);
+        }
       }
 
       // epilogue of the item: combine the two partial row sums, O_w / l -> global (each half writes its D/2 columns)
       ++tag;
       xch_put(my_slot0 + (tag & 1u) * 4096u, l_run, tag);
-      mbar_wait_warp(&o_full[w], it & 1);
+      mbar_wait(&o_full[w], it & 1);
       tc_fence_after();
       const float inv_l = 1.0f / (l_run + xch_get(peer_slot0 + (tag & 1u) * 4096u, tag));
       const int s_idx = wk.q0 + w * ATT_BQ + r;

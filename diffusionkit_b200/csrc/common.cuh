@@ -55,16 +55,23 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-// Wait until the phase with the given parity has completed.
+// Wait until the phase with the given parity has completed.  try_wait suspends the thread in hardware for ~100 clocks
+// per attempt; the retry loop is kept minimal (ncu: with a clock64() watchdog in it the polling loops of the waiting
+// warps were a quarter of all instructions the attention kernel issued).  The watchdog counts attempts instead:
+// 2^26 of them is a few seconds, then the kernel traps (a launch error instead of a hung GPU box).
+#ifndef DK_WATCHDOG_SPINS
+#define DK_WATCHDOG_SPINS (1u << 26)
+#endif
+static __device__ __noinline__ void mbar_watchdog_trap(uint64_t* bar, uint32_t parity) {
+  printf("[dkb200] mbarrier watchdog: block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+         threadIdx.x, smem_u32(bar), parity);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > DK_WATCHDOG_CYCLES) {
-      printf("[dkb200] mbarrier watchdog: block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
-    }
+    if (++spins == DK_WATCHDOG_SPINS) mbar_watchdog_trap(bar, parity);
   }
 }
 

@@ -971,6 +971,18 @@ extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* 
   return 0;
 }
 
+extern "C" int dk_groupnorm_finalize(dk_ctx* ctx, const float* partial, float* stats, int B, int G, int slots,
+                                     double count, float eps, void* stream_) {
+  DK_REQUIRE(ctx != nullptr, "dk_groupnorm_finalize: null ctx");
+  DkDeviceGuard dk_guard_(ctx);
+  DK_REQUIRE(partial != nullptr && stats != nullptr && B > 0 && G > 0 && slots > 0 && count > 0,
+             "dk_groupnorm_finalize: bad arguments");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  groupnorm_finalize_kernel<<<(B * G * 32 + 127) / 128, 128, 0, stream>>>(partial, stats, B, G, slots, count, eps);
+  DK_LAUNCH_CHECK(ctx);
+  return 0;
+}
+
 extern "C" int dk_groupnorm_apply(dk_ctx* ctx, int dtype, const void* x, void* y, const float* stats, const void* gamma,
                                   const void* beta, int B, int HW, int C, int G, int silu, void* stream_) {
   DK_REQUIRE(ctx != nullptr, "dk_groupnorm_apply: null ctx");

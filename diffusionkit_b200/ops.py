@@ -421,6 +421,65 @@ def conv3x3_s2(x, w, bias=None, out=None):
     return out
 
 
+def conv_fused_supported(H: int, W: int, Cin: int, Cout: int) -> bool:
+    return bool(_lib.load().dk_conv_fused_supported(H, W, Cin, Cout))
+
+
+def conv_up_weights(w):
+    """w [Cout,3,3,Cin] -> phase weights [4*Cout, 4*Cin] of conv3x3(nearest2x(.)) (see dk_conv_up_weights)"""
+    _chk16(w, "conv_up_weights.w")
+    Cout, _, _, Cin = w.shape
+    assert w.shape == (Cout, 3, 3, Cin) and w.is_contiguous()
+    wp = torch.empty((4 * Cout, 4 * Cin), dtype=w.dtype, device=w.device)
+    c = ctx(w.device.index)
+    c.call("dk_conv_up_weights", dtype_code(w.dtype), ptr(w), ptr(wp), Cout, Cin)
+    return wp
+
+
+def conv3x3_fused(x, w, bias=None, res=None, out=None, up: bool = False, gn=None, silu: bool = False,
+                  out_partial=None, out_G: int = 32):
+    """fused [GroupNorm+SiLU] -> [nearest 2x] -> conv3x3 (+bias, +res) -> out (+ output GroupNorm partial sums).
+    gn = (stats [B,G,2] fp32, gamma [Cin], beta [Cin], G) or None; up: w must be conv_up_weights(w3x3)."""
+    _chk16(x, "conv3x3_fused.x")
+    B, H, W, Cin = x.shape
+    if up:
+        Cout = w.shape[0] // 4
+        assert tuple(w.shape) == (4 * Cout, 4 * Cin)
+        Ho, Wo = 2 * H, 2 * W
+    else:
+        Cout = w.shape[0]
+        assert tuple(w.shape) == (Cout, 3, 3, Cin)
+        Ho, Wo = H, W
+    assert x.is_contiguous() and w.is_contiguous()
+    if out is None:
+        out = torch.empty((B, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    assert tuple(out.shape) == (B, Ho, Wo, Cout) and out.is_contiguous()
+    if res is not None:
+        assert tuple(res.shape) == tuple(out.shape) and res.is_contiguous()
+    stats = gamma = beta = None
+    G = 0
+    if gn is not None:
+        stats, gamma, beta, G = gn
+        assert stats.dtype == torch.float32 and stats.is_contiguous() and tuple(stats.shape) == (B, G, 2)
+    if out_partial is not None:
+        assert out_partial.dtype == torch.float32 and out_partial.is_contiguous()
+        assert out_partial.numel() >= B * (Ho * Wo // 128) * out_G * 2
+    c = ctx(x.device.index)
+    c.call("dk_conv3x3_fused", dtype_code(x.dtype), ptr(x), ptr(w), ptr(bias), ptr(res), ptr(out), B, H, W, Cin, Cout,
+           1 if up else 0, ptr(stats), ptr(gamma), ptr(beta), G, 1 if silu else 0, ptr(out_partial), out_G)
+    return out
+
+
+def groupnorm_finalize(partial, B: int, G: int, slots: int, count: float, eps: float = 1e-5, stats=None):
+    """partial [B, slots, G, 2] (sum, sumsq) -> stats [B, G, 2] (mean, rstd)"""
+    assert partial.dtype == torch.float32 and partial.is_contiguous()
+    if stats is None:
+        stats = torch.empty((B, G, 2), dtype=torch.float32, device=partial.device)
+    c = ctx(partial.device.index)
+    c.call("dk_groupnorm_finalize", ptr(partial), ptr(stats), B, G, slots, float(count), eps)
+    return stats
+
+
 def upsample_nearest2x(x, out=None):
     _chk16(x, "upsample.x")
     B, H, W, Cc = x.shape

@@ -213,6 +213,28 @@ int dk_conv3x3(dk_ctx* ctx, int dtype, const void* x, const void* w, const void*
  * a 4-D box traversed with element stride 2. */
 int dk_conv3x3_s2(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, void* out, int B, int H, int W,
                   int Cin, int Cout, void* stream);
+/* K7f fused ResNet-path convolution (csrc/conv_fused.cu): [GroupNorm-apply + SiLU on the input] -> [nearest 2x] ->
+ *     conv 3x3 (+ bias, + skip) -> output AND the GroupNorm partial statistics of the output, in ONE kernel.
+ *     replaces nn.GroupNorm + nn.SiLU + nn.Conv2d (+ skip) of ResnetBlock2D (vae.py:60-101) and
+ *     upsample_nearest + nn.Conv2d of the upsample stages (vae.py:20-25,146-147).
+ *     x NHWC [B,H,W,Cin] RAW (pre-norm); gn_stats [B,G,2] (mean, rstd) + gamma/beta [Cin] normalise it on the fly while
+ *     the 64-channel halo tile sits in shared memory (NULL: no norm); silu != 0 applies x*sigmoid(x) after the affine.
+ *     up == 0: w [Cout,3,3,Cin], out [B,H,W,Cout].   up == 1: conv3x3(nearest2x(x)) by sub-pixel phases,
+ *     w = the phase weights made by dk_conv_up_weights [4*Cout, 4*Cin], out [B,2H,2W,Cout].  res like out, or NULL.
+ *     out_partial [B, slots, out_G, 2], slots = output pixels / 128: (sum, sum of squares) of the STORED output per
+ *     128-pixel row segment and channel group, folded by dk_groupnorm_finalize (NULL: not wanted).
+ *     Shapes: W % 128 == 0, H % 4 == 0, Cin % 64 == 0 (<= 512), Cout % 128 == 0 — dk_conv_fused_supported says. */
+int dk_conv_fused_supported(int H, int W, int Cin, int Cout);
+int dk_conv3x3_fused(dk_ctx* ctx, int dtype, const void* x, const void* w, const void* bias, const void* res, void* out,
+                     int B, int H, int W, int Cin, int Cout, int up, const float* gn_stats, const void* gamma,
+                     const void* beta, int G, int silu, float* out_partial, int out_G, void* stream);
+/* Phase weights of conv3x3(nearest2x(.)): w [Cout,3,3,Cin] -> wp [4][Cout][2x2][Cin]; the 3x3 taps that fall on the
+ * same source pixel are added in fp32 and rounded once (2.25x fewer FLOPs than convolving the upsampled tensor). */
+int dk_conv_up_weights(dk_ctx* ctx, int dtype, const void* w, void* wp, int Cout, int Cin, void* stream);
+/* Second stage of the GroupNorm statistics: partial [B, slots, G, 2] (sum, sumsq) -> stats [B, G, 2] (mean, rstd);
+ * count = elements per (image, group).  Deterministic (fixed order, double accumulation). */
+int dk_groupnorm_finalize(dk_ctx* ctx, const float* partial, float* stats, int B, int G, int slots, double count,
+                          float eps, void* stream);
 /* nearest 2x upsample NHWC (vae.py:20-25) */
 int dk_upsample_nearest2x(dk_ctx* ctx, int dtype, const void* x, void* y, int B, int H, int W, int C, void* stream);
 /* row softmax in place: x[r, :n] = softmax(scale * x[r, :n]); fp32 math, 16-bit storage (vae.py:49-52) */
