@@ -227,9 +227,12 @@ def run_ours(args):
     # weights: rank 0 materialises the synthetic parameters, one NCCL broadcast replicates them (the only collective)
     specs = mmdit_param_specs(cfg)
     t0 = time.time()
-    params = dkd.replicate_params(specs, lambda: init_params(specs, seed=0, dtype=dtype, device=dev), dtype, dev)
+    wt = {}
+    params = dkd.replicate_params(specs, lambda: init_params(specs, seed=0, dtype=dtype, device=dev), dtype, dev,
+                                  timings=wt)
     vspecs = vae_decoder_param_specs(VAEDecoderConfig())
-    vparams = dkd.replicate_params(vspecs, lambda: init_params(vspecs, seed=1, dtype=dtype, device=dev), dtype, dev)
+    vparams = dkd.replicate_params(vspecs, lambda: init_params(vspecs, seed=1, dtype=dtype, device=dev), dtype, dev,
+                                   timings=wt)
     torch.cuda.synchronize()
     t_weights = time.time() - t0
     Pipe = dk.FluxPipeline if kind == "flux" else dk.DiffusionPipeline
@@ -294,7 +297,16 @@ def run_ours(args):
     clk = clocks.stop()
     split["denoise"] = split["ev"][0].elapsed_time(split["ev"][1])
     split["decode"] = split["ev"][1].elapsed_time(split["ev"][2])
-    t_dev = dkd.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    t_mine = e0.elapsed_time(e1) / 1e3
+    t_dev = dkd.max_over_ranks(t_mine, dev)
+    # per-rank device times of the timed region (the max is the metric; the spread attributes the N > 1 efficiency loss)
+    per_rank = [t_mine]
+    if world > 1:
+        import torch.distributed as tdist
+
+        buf = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        tdist.all_gather(buf, torch.tensor([t_mine], dtype=torch.float64, device=dev))
+        per_rank = [float(b.item()) for b in buf]
 
     # ---- timed region 2: end to end through the public API with host inputs / outputs
     step_e2e()  # warm the host-side path (pinned staging, PIL)
@@ -371,7 +383,10 @@ def run_ours(args):
         "mmdit_tensor_frac_sustained": mmdit_frac,
         "last_step_ms": {"denoise": split["denoise"], "decode": split["decode"]},
         "denoise_tflops_per_image": flops_img / 1e12,
+        "per_rank_step_ms": [round(t / args.steps * 1e3, 3) for t in per_rank],
         "weights_init_broadcast_s": t_weights,
+        # the one-time weight replication, split: lazy NCCL communicator creation / rank-0 init / the broadcast itself
+        "weights_timing": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in wt.items()},
     }
     if world == 1 and not args.no_cpu_baseline:
         try:

@@ -343,28 +343,48 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
       }
       // pass 2: P = exp2(s * sl2 - m_run) written over this half's OWN score columns (16 packed columns per 32 keys), so
       // no thread ever overwrites scores another thread still has to read
+      // (the tail mask lives in a branch of its own: as a per-element select inside the main loop it was 26 % of all
+      //  instructions the kernel issued — ncu, ISETP + FSEL — on every step of every tile)
       float ls0 = 0.f, ls1 = 0.f;
+      if (kv_valid >= 64) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t sc[32];
-        tmem_ld_32x32(t_s + c * 32, sc);
-        tmem_ld_wait();
-        uint32_t pk[16];
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sc[32];
+          tmem_ld_32x32(t_s + c * 32, sc);
+          tmem_ld_wait();
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
-          if (kv_valid < 64) {
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = fmaf(__uint_as_float(sc[2 * i]), sl2, -m_run);
+            const float x1 = fmaf(__uint_as_float(sc[2 * i + 1]), sl2, -m_run);
+            const float e0 = ex2_approx(x0);
+            const float e1 = (POLY4 == 2 || (POLY4 == 1 && (i & 1))) ? ex2_poly(x1) : ex2_approx(x1);
+            ls0 += e0;
+            ls1 += e1;
+            pk[i] = H16::pack(e0, e1);
+          }
+          tmem_st_32x16(t_s + c * 16, pk);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sc[32];
+          tmem_ld_32x32(t_s + c * 32, sc);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a0 = __uint_as_float(sc[2 * i]), a1 = __uint_as_float(sc[2 * i + 1]);
             if (c * 32 + 2 * i >= kv_valid) a0 = -INFINITY;
             if (c * 32 + 2 * i + 1 >= kv_valid) a1 = -INFINITY;
+            const float e0 = ex2_approx(fmaf(a0, sl2, -m_run));
+            const float e1 = ex2_approx(fmaf(a1, sl2, -m_run));
+            ls0 += e0;
+            ls1 += e1;
+            pk[i] = H16::pack(e0, e1);
           }
-          const float x0 = fmaf(a0, sl2, -m_run), x1 = fmaf(a1, sl2, -m_run);
-          const float e0 = ex2_approx(x0);
-          const float e1 = (POLY4 == 2 || (POLY4 == 1 && (i & 1))) ? ex2_poly(x1) : ex2_approx(x1);
-          ls0 += e0;
-          ls1 += e1;
-          pk[i] = H16::pack(e0, e1);
+          tmem_st_32x16(t_s + c * 16, pk);
         }
-        tmem_st_32x16(t_s + c * 16, pk);
       }
       l_run += ls0 + ls1;
       tmem_st_wait();

@@ -232,7 +232,7 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], (p.debug & 4) ? 256 : 8);
+      mbar_init(&p_full[i], (p.debug & 4) ? 8 : 256);
       mbar_init(&o_full[i], 1);
       mbar_init(&o_empty[i], 8);
     }
@@ -267,7 +267,7 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       // Q tiles of this item: wait until the previous item's QK MMAs no longer read the buffers
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        mbar_wait_warp(&q_empty[w], (it & 1) ^ 1);
+        mbar_wait(&q_empty[w], (it & 1) ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&q_full[w], Cfg::TILE_BYTES);
 #pragma unroll
@@ -279,7 +279,7 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
       }
       for (int j = 0; j < n_tiles; ++j) {
         const int kv_row = row_base + j * ATT_BKV;
-        mbar_wait_warp(&k_empty[st], par ^ 1);
+        mbar_wait(&k_empty[st], par ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&k_full[st], Cfg::TILE_BYTES);
 #pragma unroll
@@ -287,7 +287,7 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
             tma_load_2d(sK + st * Cfg::TILE_BYTES + a * 16384, &tmQKV, &k_full[st], h + wk.head * D + a * 64, kv_row);
         }
         __syncwarp();
-        mbar_wait_warp(&v_empty[st], par ^ 1);
+        mbar_wait(&v_empty[st], par ^ 1);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(&v_full[st], Cfg::TILE_BYTES);
 #pragma unroll
@@ -340,10 +340,10 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
     for (int it = 0; it < my_items; ++it) {
       // first QK of the item: needs Q, K(0); S_w is free because the previous item's last PV_w (which read P_w from
       // those columns) was issued earlier by this thread
-      mbar_wait_warp(&k_full[st], par);
+      mbar_wait(&k_full[st], par);
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        mbar_wait_warp(&q_full[w], it & 1);
+        mbar_wait(&q_full[w], it & 1);
         tc_fence_after();
         if (elect_one_sync()) {
           issue_qk(w, st);
@@ -355,10 +355,10 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
         const int st_n = (st + 1 == KS) ? 0 : st + 1;
         const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
         const bool more = j + 1 < n_tiles;
-        mbar_wait_warp(&v_full[st], par);
-        if (j == 0) mbar_wait_warp(&o_empty[0], (it & 1) ^ 1);   // O_0 of the previous item drained
-        mbar_wait_warp(&p_full[0], step & 1);
-        if (more) mbar_wait_warp(&k_full[st_n], par_n);
+        mbar_wait(&v_full[st], par);
+        if (j == 0) mbar_wait(&o_empty[0], (it & 1) ^ 1);   // O_0 of the previous item drained
+        mbar_wait(&p_full[0], step & 1);
+        if (more) mbar_wait(&k_full[st_n], par_n);
         tc_fence_after();
         if (elect_one_sync()) {
           issue_pv(0, st, j == 0);
@@ -370,8 +370,8 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
           }
         }
         __syncwarp();
-        if (j == 0) mbar_wait_warp(&o_empty[1], (it & 1) ^ 1);
-        mbar_wait_warp(&p_full[1], step & 1);
+        if (j == 0) mbar_wait(&o_empty[1], (it & 1) ^ 1);
+        mbar_wait(&p_full[1], step & 1);
         tc_fence_after();
         if (elect_one_sync()) {
           issue_pv(1, st, j == 0);
@@ -422,11 +422,11 @@ attention_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
                            my_slot0 + par_off, peer_slot0 + par_off, tag);
         tmem_st_wait();
         tc_fence_before();
-        if (p.debug & 4) {
-          mbar_arrive(&p_full[w]);
-        } else {
+        if (p.debug & 4) {          // experiment: one arrival per warp (measured slower than 256 per-thread arrivals)
           __syncwarp();
           if (lane == 0) mbar_arrive(&p_full[w]);
+        } else {
+          mbar_arrive(&p_full[w]);
         }
       }
 

@@ -70,7 +70,6 @@ struct ConvFParams {
   int silu;
   float* out_partial;   // [B, slots, out_G, 2] per-(128-pixel row segment, group) (sum, sumsq) of the output, or null
   int out_G;
-  int flags;            // bit 0: set the descriptor base-offset field for line-shifted operands
 };
 
 __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0,
@@ -227,7 +226,6 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const uint32_t desc_hi = smem_desc_hi_sw128(1024);
       const uint32_t a_addr0 = smem_u32(sA);
       const uint32_t b_lo0 = smem_desc_lo(smem_u32(sB), 0);
-      const bool use_base_off = (p.flags & 1) != 0;
       uint32_t bst = 0, bph = 0, abuf = 0, aph = 0, n_it = 0;
       for (int item = pair_id; item < total_items; item += num_pairs, ++n_it) {
         CfItem it;
@@ -250,13 +248,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 #pragma unroll
               for (int rr = 0; rr < CF_R; ++rr) {
                 const uint32_t a_addr = a_addr0 + abuf * CF_A_BYTES + ((rr + dy) * CF_HW + dx) * 128;
-                // line-shifted start: the swizzle phase of the first line is (address >> 7) & 7
-                const uint32_t hi = desc_hi | (use_base_off ? (((a_addr >> 7) & 7u) << 17) : 0u);
+                // line-shifted start address, descriptor base-offset field left 0: the 128B swizzle is a function of the
+                // shared-memory ADDRESS bits (chunk ^= line & 7), for the TMA write and for the operand read alike —
+                // verified on hardware (setting base offset = (address >> 7) & 7 produces wrong results)
                 const uint32_t a_lo = smem_desc_lo(a_addr, 0);
                 const uint32_t d_tmem = tmem_base + acc * (CF_R * CF_BN) + rr * CF_BN;
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_ss_pair(d_tmem, smem_desc_join(a_lo + k * 2, hi), smem_desc_join(b_lo + k * 2, desc_hi), idesc,
+                  umma_ss_pair(d_tmem, smem_desc_join(a_lo + k * 2, desc_hi), smem_desc_join(b_lo + k * 2, desc_hi), idesc,
                                (cb | tap | k) != 0 ? 1u : 0u);
               }
               umma_commit_pair(&b_empty[bst], 3);
@@ -571,8 +570,6 @@ extern "C" int dk_conv3x3_fused(dk_ctx* ctx, int dtype, const void* x, const voi
   p.silu = silu;
   p.out_partial = out_partial;
   p.out_G = out_G;
-  static const int base_off = [] { const char* v = getenv("DK_CONV_BASE_OFFSET"); return v ? atoi(v) : 0; }();
-  p.flags = base_off ? 1 : 0;
 
   CUtensorMap tmX, tmW;
   {

@@ -59,22 +59,67 @@ def pack_arena(specs: Sequence[Spec], dtype: torch.dtype, device) -> Tuple[torch
     return arena, views
 
 
-def replicate_params(specs: Sequence[Spec], init_fn, dtype: torch.dtype, device, src: int = 0) -> Dict[str, torch.Tensor]:
-    """Rank `src` materialises the parameters (init_fn() -> dict name -> tensor) into the arena; one broadcast
-    replicates them to every rank.  With world size 1 this is just init + pack."""
-    arena, views = pack_arena(specs, dtype, device)
+_comm_ready = False
+
+
+def warm_up_communicator(device) -> float:
+    """Force the lazy NCCL communicator creation (ring/tree discovery, NVLS setup: seconds at 8 ranks) with a 1-element
+    all-reduce so that it is not billed to the weight broadcast.  -> seconds spent (0 when already done / single rank)."""
+    global _comm_ready
+    import time
+
+    if _comm_ready or not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0.0
+    t0 = time.time()
+    t = torch.zeros(1, device=device)
+    dist.all_reduce(t)
+    if t.is_cuda:
+        torch.cuda.synchronize(device)
+    _comm_ready = True
+    return time.time() - t0
+
+
+def replicate_params(specs: Sequence[Spec], init_fn, dtype: torch.dtype, device, src: int = 0,
+                     timings: Dict[str, float] | None = None) -> Dict[str, torch.Tensor]:
+    """Rank `src` materialises the parameters (init_fn() -> dict name -> tensor) into the arena; ONE pass of broadcasts
+    over the packed arena replicates them to every rank (NCCL over NVLink / NVSwitch; chunks of < 2^31 elements, the
+    collective's count limit).  With world size 1 this is just init + pack.
+    timings (optional dict) receives comm_init_s / init_s / broadcast_s / broadcast_gbs, accumulated over calls."""
+    import time
+
+    def sync():
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)
+
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
+    t_comm = warm_up_communicator(device)
+    arena, views = pack_arena(specs, dtype, device)
+    t0 = time.time()
     if rank == src:
         params = init_fn()
         for name, v in views.items():
             v.copy_(params[name].to(device=v.device, dtype=dtype))
         del params
+    sync()
+    t_init = time.time() - t0
+    t_bc = 0.0
     if world > 1:
-        # chunked so that no single collective exceeds 2^31 elements
-        step = 1 << 30
+        dist.barrier()                      # the broadcast is timed from the moment the source data exists
+        sync()
+        t0 = time.time()
+        step = (1 << 31) - 16
         for off in range(0, arena.numel(), step):
             dist.broadcast(arena[off:off + step], src=src)
+        sync()
+        t_bc = time.time() - t0
+    if timings is not None:
+        timings["comm_init_s"] = timings.get("comm_init_s", 0.0) + t_comm
+        timings["init_s"] = timings.get("init_s", 0.0) + t_init
+        timings["broadcast_s"] = timings.get("broadcast_s", 0.0) + t_bc
+        timings["broadcast_bytes"] = timings.get("broadcast_bytes", 0) + (arena.numel() * arena.element_size() if world > 1 else 0)
+        if timings["broadcast_s"] > 0:
+            timings["broadcast_gbs"] = timings["broadcast_bytes"] / timings["broadcast_s"] / 1e9
     return views
 
 

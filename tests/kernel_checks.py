@@ -819,13 +819,6 @@ def check_conv_fused():
     return out
 
 
-def check_conv_fused_base_offset():
-    """the same cases with the descriptor base-offset field set for line-shifted operands (DK_CONV_BASE_OFFSET=1):
-    exactly one of the two encodings can be right on hardware — kept as an experiment until the other is deleted"""
-    os.environ["DK_CONV_BASE_OFFSET"] = "1"
-    return check_conv_fused()
-
-
 def check_fullsize_conv_fused():
     """the fused ResNet-path convolution at the 1024^2 decode's real extents"""
     _setup()
@@ -1015,7 +1008,7 @@ def check_fullsize_groupnorm():
 
 
 FULLSIZE_CHECKS = [check_fullsize_gemm_fc1, check_fullsize_gemm_single_out, check_fullsize_gemm_qkv_fused,
-                   check_fullsize_attention, check_fullsize_conv, check_fullsize_groupnorm]
+                   check_fullsize_attention, check_fullsize_conv, check_fullsize_groupnorm, check_fullsize_conv_fused]
 
 
 ALL_CHECKS = [
@@ -1024,13 +1017,13 @@ ALL_CHECKS = [
     check_gemm_pair_kernel, check_gemm_pair_legacy_store, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
     check_text_kernels, check_attention_small,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
-    check_attention_v1_kernel, check_attention_v2_kernel,
+    check_attention_v1_kernel, check_attention_v2_kernel, check_conv_fused,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,
 ] + FULLSIZE_CHECKS
 
 # kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
 # suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
-EXPERIMENTAL_CHECKS = [check_conv_fused, check_conv_fused_base_offset, check_fullsize_conv_fused, check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel,
+EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel,
                        check_attention_v5_kernel]
 

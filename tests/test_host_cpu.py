@@ -270,6 +270,30 @@ def test_header_is_plain_c(tmp_path):
         assert "|0|" not in out.stdout          # no device here: create fails with a message instead of crashing
 
 
+def test_integration_doc_struct_is_current():
+    """INTEGRATION.md's ctypes stub of struct dk_gemm_args is the generated one (a stale, shorter stub makes dk_gemm read
+    past the end of the caller's struct), and the binding it is generated from has the header's fields in the header's order"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import re
+
+    import gen_integration_stub as gen
+
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    assert gen.block() in doc, "run tools/gen_integration_stub.py and paste its output into INTEGRATION.md section 2"
+    hdr = open(os.path.join(ROOT, "include", "dkb200.h")).read()
+    body = hdr[hdr.index("typedef struct dk_gemm_args"):hdr.index("} dk_gemm_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        first, *rest = decl.split(",")
+        names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", first.strip())[0])
+        names += [r.strip().lstrip("*").strip() for r in rest]
+    assert names == [n for n, _ in _lib.GemmArgs._fields_], (names, [n for n, _ in _lib.GemmArgs._fields_])
+
+
 def test_attention_v4_protocol_model():
     """csrc/attention_v4.cu (experimental, one Q tile per CTA with a double-buffered score accumulator) has its barrier
     protocol and arithmetic mirrored in tools/sim_attention_v4.py; under random interleavings it must neither deadlock
