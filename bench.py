@@ -58,15 +58,15 @@ def mmdit_flops_per_forward(cfg, n_img, n_txt):
 
 
 def committed_gemm_traffic():
-    """dram__bytes_read + dram__bytes_write of ONE launch of the dominant kernel (gemm2_tc_kernel on the largest C4
-    shape, 16384 x 12288 x 3072 + GELU) from the committed `ncu --set full` capture; algorithmic bytes of that launch are
-    (16384 + 12288) * 3072 * 2 + 16384 * 12288 * 2 = 579 MB."""
+    """dram__bytes_read + dram__bytes_write of ONE launch of the dominant kernel (gemm2_tc_kernel, default configuration,
+    on the largest C4 shape, 16384 x 12288 x 3072 + GELU) from the committed ncu capture of the kernel as it is timed
+    here; algorithmic bytes of that launch are (16384 + 12288) * 3072 * 2 + 16384 * 12288 * 2 = 579 MB."""
     try:
-        rows = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_final.json")))
-        for r in rows:
-            if "gemm2_tc_kernel" in r.get("Kernel Name []", ""):
-                mb = float(r["dram__bytes_read.sum [Mbyte]"]) + float(r["dram__bytes_write.sum [Mbyte]"])
-                return mb * 1e6, "profiles/r01_ncu_full_final.json: gemm2_tc_kernel 16384x12288x3072, bytes per launch"
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_gemm_dram.json")))
+        for r in d["rows"]:
+            if r["config"] == "base" and r["shape_MNK"].startswith("16384 12288 3072"):
+                return float(r["dram_bytes_total"]), ("profiles/r02_ncu_gemm_dram.json: gemm2_tc_kernel (default config) "
+                                                      "16384x12288x3072+GELU, bytes per launch")
     except Exception:
         pass
     return None, None

@@ -11,7 +11,7 @@
 // same shared-memory tile read through a UMMA descriptor whose start address is shifted by whole lines.  Every input
 // byte crosses L2 -> SM once per 64-channel block and n-tile (round 1: nine times).
 //
-// Because the halo is staged once, the GroupNorm affine + SiLU can run ON it: four transform warps rewrite the tile in
+// Because the halo is staged once, the GroupNorm affine + SiLU can run ON it: six transform warps rewrite the tile in
 // place (normalise with the per-(image, channel) scale/shift table, SiLU with one MUFU.TANH, back to 16 bits; padding
 // pixels stay zero, as the reference pads AFTER the activation) before the MMAs read it — once per input element, not
 // once per tap.
@@ -25,11 +25,14 @@
 // its own halo and HALF of every 128 x 64 weight tile; shared-memory operand traffic per MMA is 96 B/clk instead of
 // the 128 B/clk a single-CTA 128 x 128 tile needs (the 1024^2 x 128-channel layers ran at 0.85 PFLOP/s for that reason).
 //
-//   warp 0      TMA producer   halo boxes (double buffered per 64-channel block) and weight half-tiles (ring)
-//   warp 1      MMA issuer     leader CTA only
-//   warp 2      TMEM allocator 512 columns: 2 accumulator sets x R rows x 128 channels
+//   warp 14     TMA producer   halo boxes (double buffered per 64-channel block) and weight half-tiles (ring);
+//                              also allocates TMEM: 512 columns = 2 accumulator sets x R rows x 128 channels
+//   warp 15     MMA issuer     leader CTA only
 //   warps 4-11  epilogue       bias, skip, store, per-(pixel row, group) statistics of the stored values
-//   warps 12-15 transform      GroupNorm affine + SiLU in place on the halo (or a pass-through when there is no norm)
+//   warps 0-3, 12, 13 transform  GroupNorm affine + SiLU in place on the halo (a pass-through when there is no norm)
+// The schedulers favour the highest warp id of their quarter, so the single-thread MMA issuer and the TMA producer sit
+// ABOVE every other warp: with the issuer as warp 1 the mere loop skeleton of a busy transform warp on the same
+// scheduler cost 25 % of the kernel's throughput (measured).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -46,6 +49,7 @@ constexpr int CF_A_BYTES = CF_HR * CF_HW * 128;        // 66,560 (65 KB) per 64-
 constexpr int CF_B_BYTES = (CF_BN / 2) * 64 * 2;       // 8 KB: this CTA's half of one tap's weight tile
 constexpr int CF_B_STAGES = 5;
 constexpr int CF_THREADS = 512;
+constexpr int CF_TWARPS = 6;                           // transform warps: 0-3, 12, 13
 constexpr int CF_TABLE_BYTES = 512 * 2 * 4;            // per-channel (scale, shift), Cin <= 512
 constexpr int CF_STAT_BYTES = 2 * 8 * CF_R * 2 * 8 * 2 * 4;   // [parity][warp][row][chunk][group<=8][sum,sumsq]
 constexpr int CF_OFF_B = 2 * CF_A_BYTES;
@@ -68,6 +72,7 @@ struct ConvFParams {
   const void* beta;
   int G;
   int silu;
+  int debug;            // timing experiments (DK_CF_DEBUG): 1 transform = load/store only, 2 = math only, 3 = neither
   float* out_partial;   // [B, slots, out_G, 2] per-(128-pixel row segment, group) (sum, sumsq) of the output, or null
   int out_G;
 };
@@ -103,11 +108,42 @@ __device__ __forceinline__ void cf_decode(const ConvFParams& p, int item, CfItem
   it.b = item / p.tiles_y;
 }
 
+// Sum N values (N = 16, 8 or 4) over the 32 lanes of a warp with N + log-many shuffles instead of 5 N: at every step a
+// lane keeps one half of its values and hands the other half to its partner (recursive halving), then the last value is
+// reduced over the remaining lane bits.  On return lane l holds in v[0] the complete sum of value index
+// warp_multi_index<N>(l); lanes that differ only in the low (plain-reduced) bits hold copies.
+template <int N>
+__device__ __forceinline__ void warp_multi_sum(float (&v)[N], int lane) {
+  int off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float keep = hi ? v[i + n / 2] : v[i];
+      const float send = hi ? v[i] : v[i + n / 2];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+#pragma unroll
+  for (; off > 0; off >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+}
+template <int N>
+__device__ __forceinline__ int warp_multi_index(int lane) {
+  int idx = 0, off = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, off >>= 1) idx += (lane & off) ? n / 2 : 0;
+  return idx;
+}
+
 // per group of CPG channels of one 32-channel chunk: sum and sum of squares over the warp's 32 pixels -> dst[g][2]
 template <int CPG>
 __device__ __forceinline__ void cf_chunk_stats(const float (&v)[32], float* dst, int lane) {
+  constexpr int NG = 32 / CPG;          // groups in the chunk
+  constexpr int N = 2 * NG;             // values to reduce: NG sums then NG sums of squares
+  float a[N];
 #pragma unroll
-  for (int g = 0; g < 32 / CPG; ++g) {
+  for (int g = 0; g < NG; ++g) {
     float s = 0.f, q = 0.f;
 #pragma unroll
     for (int c = 0; c < CPG; ++c) {
@@ -115,12 +151,15 @@ __device__ __forceinline__ void cf_chunk_stats(const float (&v)[32], float* dst,
       s += t;
       q = fmaf(t, t, q);
     }
-    s = warp_sum(s);
-    q = warp_sum(q);
-    if (lane == 0) {
-      dst[g * 2] = s;
-      dst[g * 2 + 1] = q;
-    }
+    a[g] = s;
+    a[NG + g] = q;
+  }
+  warp_multi_sum<N>(a, lane);
+  constexpr int LOW = 32 / N;           // lanes per value (copies)
+  if ((lane & (LOW - 1)) == 0) {
+    const int idx = warp_multi_index<N>(lane);
+    const int g = idx % NG, which = idx / NG;
+    dst[g * 2 + which] = a[0];
   }
 }
 
@@ -155,14 +194,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int cblocks = p.Cin / 64;
   const int ntaps = p.up ? 4 : 9;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 14 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == 15 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_land[i], 1);
-      mbar_init(&a_ready[i], 8);
+      mbar_init(&a_ready[i], 2 * CF_TWARPS);
       mbar_init(&a_empty[i], 1);
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 16);
@@ -174,7 +213,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     fence_barrier_init();
   }
   cluster_sync_all();
-  if (warp == 2) {
+  if (warp == 14) {
     tmem_alloc_pair(tmem_slot, 512);
     tmem_relinquish_pair();
   }
@@ -183,7 +222,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == 14) {
     // ------------------------------------------------------------------ TMA producer (both CTAs), converged warp
     uint32_t bst = 0, bph = 0;     // weight ring
     uint32_t abuf = 0, aph = 0;    // halo double buffer
@@ -219,7 +258,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 15) {
     if (leader) {
       // ---------------------------------------------------------------- MMA issuer (leader CTA only), converged warp
       constexpr uint32_t idesc = make_idesc_f16(256, CF_BN, H16::is_bf16, false, false);
@@ -277,10 +316,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp < 4 || warp >= 12) {
     // ------------------------------------------------------------------ transform warps: GroupNorm affine + SiLU in place
-    const int tw = warp - 12;
-    const int tid = tw * 32 + lane;            // 0..127
+    // Six warps (192 threads); a thread owns one logical 16-byte chunk (8 channels) of every 24th halo pixel, two pixels
+    // per iteration with both shared-memory loads issued first.  Budget per 64-channel block: the MMAs of the block take
+    // 9 taps x 2 rows x 256 clk = 4608 clk; 33,280 halo elements need 2080 clk of MUFU.TANH (16 / clk / SM).
+    const int tw = warp >= 12 ? warp - 8 : warp;         // 0..5
+    const int tid = tw * 32 + lane;                       // 0..191
+    constexpr int TT = CF_TWARPS * 32;
     const int chunk = tid & 7;                 // logical 16-byte chunk = 8 channels of the 64-channel block
     const int cpg = p.gn_stats != nullptr ? p.Cin / p.G : 1;
     uint32_t abuf = 0, aph = 0;
@@ -292,8 +335,8 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int x0 = it.tx * CF_TW;
       if (p.gn_stats != nullptr && it.b != cur_b) {
         // per-channel (scale, shift) of this image: y = x * (rstd * gamma) + (beta - mean * rstd * gamma)
-        named_bar_sync(2, 128);                // nobody still reads the previous image's table
-        for (int c = tid; c < p.Cin; c += 128) {
+        named_bar_sync(2, TT);                 // nobody still reads the previous image's table
+        for (int c = tid; c < p.Cin; c += TT) {
           const int g = c / cpg;
           const float mean = p.gn_stats[(it.b * p.G + g) * 2], rstd = p.gn_stats[(it.b * p.G + g) * 2 + 1];
           const float ga = H16::to_f(reinterpret_cast<const T*>(p.gamma)[c]);
@@ -301,11 +344,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           table[2 * c] = rstd * ga;
           table[2 * c + 1] = be - mean * rstd * ga;
         }
-        named_bar_sync(2, 128);
+        named_bar_sync(2, TT);
         cur_b = it.b;
       }
       for (int cb = 0; cb < cblocks; ++cb) {
-        mbar_wait_warp(&a_land[abuf], aph);
+        mbar_wait(&a_land[abuf], aph);
         if (p.gn_stats != nullptr) {
           float sc[8], sh[8];
 #pragma unroll
@@ -314,28 +357,45 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             sh[j] = table[2 * (cb * 64 + chunk * 8 + j) + 1];
           }
           const uint32_t base = smem_u32(sA) + abuf * CF_A_BYTES;
-          for (int q = tid >> 3; q < CF_HR * CF_HW; q += 16) {
+          const bool do_silu = p.silu != 0;
+          // padding pixels (outside the image) stay zero: the reference pads AFTER the activation
+          auto in_image = [&](int q) {
             const int hr = q / CF_HW, hx = q - hr * CF_HW;
             const int gy = y0 - 1 + hr, gx = x0 - 1 + hx;
-            if (gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) continue;   // zero padding stays zero (applied after the activation)
-            const uint32_t addr = base + q * 128 + ((chunk ^ (q & 7)) << 4);
-            uint32_t w[4];
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(addr));
+            return q < CF_HR * CF_HW && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+          };
+          auto xform = [&](uint32_t (&w)[4]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float2 f = H16::unpack(w[i]);
-              float a = H16::to_f(H16::from_f(fmaf(f.x, sc[2 * i], sh[2 * i])));       // GroupNorm output, 16-bit like MLX
-              float b = H16::to_f(H16::from_f(fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1])));
-              if (p.silu) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op per element
+              float a = fmaf(f.x, sc[2 * i], sh[2 * i]);
+              float b = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
+              if (do_silu) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op per element
                 const float ha = 0.5f * a, hb = 0.5f * b;
                 a = fmaf(ha, tanh_approx(ha), ha);
                 b = fmaf(hb, tanh_approx(hb), hb);
               }
               w[i] = H16::pack(a, b);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          };
+          for (int q0 = (p.debug & 8) ? CF_HR * CF_HW : (tid >> 3); q0 < CF_HR * CF_HW; q0 += 2 * (TT / 8)) {
+            const int q1 = q0 + TT / 8;
+            const bool ok0 = in_image(q0), ok1 = in_image(q1);
+            const uint32_t addr0 = base + q0 * 128 + ((chunk ^ (q0 & 7)) << 4);
+            const uint32_t addr1 = base + q1 * 128 + ((chunk ^ (q1 & 7)) << 4);
+            uint32_t w0[4] = {0u, 0u, 0u, 0u}, w1[4] = {0u, 0u, 0u, 0u};
+            const bool mem = !(p.debug & 2), math = !(p.debug & 1);
+            if (ok0 && mem) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0[0]), "=r"(w0[1]), "=r"(w0[2]), "=r"(w0[3]) : "r"(addr0));
+            if (ok1 && mem) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w1[0]), "=r"(w1[1]), "=r"(w1[2]), "=r"(w1[3]) : "r"(addr1));
+            if (math) {
+              xform(w0);
+              xform(w1);
+            }
+            if (ok0 && mem) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr0), "r"(w0[0]), "r"(w0[1]), "r"(w0[2]), "r"(w0[3]) : "memory");
+            if (ok1 && mem) asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr1), "r"(w1[0]), "r"(w1[1]), "r"(w1[2]), "r"(w1[3]) : "memory");
+            if (!mem && (w0[0] ^ w1[3]) == 0x12345u) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr0), "r"(w0[1]) : "memory");   // keep the math alive
           }
-          fence_proxy_async_smem();             // generic-proxy writes -> visible to the tensor core's operand reads
+          if (!(p.debug & 4)) fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core's operand reads
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&a_ready[abuf]), 0));
@@ -468,7 +528,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   tc_fence_before();
   cluster_sync_all();
-  if (warp == 2) {
+  if (warp == 14) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }
@@ -570,6 +630,8 @@ extern "C" int dk_conv3x3_fused(dk_ctx* ctx, int dtype, const void* x, const voi
   p.silu = silu;
   p.out_partial = out_partial;
   p.out_G = out_G;
+  static const int dbg = [] { const char* v = getenv("DK_CF_DEBUG"); return v ? atoi(v) : 0; }();
+  p.debug = dbg;
 
   CUtensorMap tmX, tmW;
   {

@@ -4,14 +4,14 @@
 //   out = epilogue( conv3x3(x NHWC, w OHWI) )  (nn.Conv2d — reference mlx/vae.py:73-81,134-136,349-351,384)
 //
 // Structure (one CTA per SM, 256 threads):
-//   warp 0 : TMA producer     — streams 128x64 A tiles and BNx64 W tiles (128B swizzle) through a STAGES-deep
+//   warp 10: TMA producer     — streams 128x64 A tiles and BNx64 W tiles (128B swizzle) through a STAGES-deep
 //                               mbarrier ring.  For the convolution the A tile of tap (dy,dx) is a shifted 4-D
 //                               TMA box of the NHWC input; out-of-bounds elements are zero-filled by the TMA
 //                               unit, which *is* the zero padding — no im2col buffer exists anywhere.
-//   warp 1 : MMA issuer       — one thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator;
+//   warp 11: MMA issuer       — one thread issues tcgen05.mma (M=128, N=BN, K=16) into a TMEM accumulator;
 //                               tcgen05.commit releases smem stages / publishes the accumulator.
-//   warp 2 : TMEM allocator   — 2*BN columns: two accumulators, so tile i+1's mainloop overlaps tile i's epilogue.
-//   warps 4-11: epilogue      — tcgen05.ld (lane = row; two warps per TMEM lane quarter, each owning half of the
+//   warp 8 : TMEM allocator   — 2*BN columns: two accumulators, so tile i+1's mainloop overlaps tile i's epilogue.
+//   warps 0-7 : epilogue      — tcgen05.ld (lane = row; two warps per TMEM lane quarter, each owning half of the
 //                               tile's columns), fused bias / GELU-erf / adaLN gate / residual, or QK-RMSNorm + RoPE
 //                               on the q/k thirds of a packed QKV projection; 128-bit stores straight to the
 //                               destination row (row remap = joint-sequence scatter).
@@ -26,7 +26,10 @@ namespace dk {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue (2 per TMEM lane quarter)
+// warps 0-7: epilogue (2 per TMEM lane quarter); 8: TMEM allocator; 10: TMA producer; 11: MMA issuer — the schedulers
+// favour the highest warp id of their quarter, so the issuer and the producer sit above the epilogue warps
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_W_ALLOC = 8, GEMM_W_TMA = 10, GEMM_W_MMA = 11;
 
 template <int BN>
 struct GemmCfg {
@@ -65,11 +68,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = threadIdx.x & 31;
   const int total_tiles = s.num_m * s.num_n;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == GEMM_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == GEMM_W_MMA && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -80,7 +83,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == GEMM_W_ALLOC) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -102,7 +105,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     n_blk = in_group / gsz;
   };
 
-  if (warp == 0) {
+  if (warp == GEMM_W_TMA) {
     // ------------------------------------------------------------------ TMA producer, converged warp
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -145,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == GEMM_W_MMA) {
     // -------------------------------------------------------------------- MMA issuer, converged warp
     constexpr uint32_t idesc = make_idesc_f16(BM, BN, H16::is_bf16, false, B_MN);
     const uint32_t desc_hi = smem_desc_hi_sw128(1024);
@@ -180,10 +183,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue (256 threads, lane = tile row)
     const int quarter = warp & 3;          // TMEM lanes 32*quarter .. 32*quarter+31 are accessible to this warp
-    const int half = (warp - 4) >> 2;      // which half of the tile's columns this warp drains
+    const int half = warp >> 2;            // which half of the tile's columns this warp drains
     constexpr int NCH = BN / 64;           // 32-column chunks per warp
     const int r_in_tile = quarter * 32 + lane;
     uint32_t it = 0;
@@ -235,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == GEMM_W_ALLOC) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -11,7 +11,8 @@ def timeit(fn, iters=20, warm=5):
     for _ in range(iters): fn()
     e.record(); torch.cuda.synchronize()
     return s.elapsed_time(e) / iters / 1e3
-for name, (B, S, heads, d) in {"c4": (4, 4352, 24, 128), "c2": (1, 1280, 24, 128), "sd3": (8, 4685, 24, 64)}.items():
+if __name__ == "__main__":
+  for name, (B, S, heads, d) in {"c4": (4, 4352, 24, 128), "c2": (1, 1280, 24, 128), "sd3": (8, 4685, 24, 64)}.items():
     dt = torch.bfloat16 if d == 128 else torch.float16
     qkv = torch.randn((B * S, 3 * heads * d), device=DEV, dtype=dt)
     o = torch.empty((B * S, heads * d), device=DEV, dtype=dt)
