@@ -563,7 +563,9 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
     const char* e = getenv("DK_ATTENTION_IMPL");
     return e != nullptr && e[0] == '5';
   }();
-  if (use_v5) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
+  // default per head dim (same-box A/B, round 2): d = 64 (SD3) -> v5, 646 vs 570 TFLOP/s; d = 128 (FLUX) -> v3, 1133 vs 1121
+  static const bool impl_unset = getenv("DK_ATTENTION_IMPL") == nullptr;
+  if (use_v5 || (impl_unset && d == 64)) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
   if (legacy_impl != 0) return dk_launch_attention_legacy(ctx, legacy_impl, dtype, d, tm, p, stream);
   if (dtype == DK_BF16) {
     if (d == 128) return launch_attention_v3<__nv_bfloat16, 128>(ctx, tm, p, stream);

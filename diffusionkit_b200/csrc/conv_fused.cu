@@ -28,8 +28,8 @@
 //   warp 14     TMA producer   halo boxes (double buffered per 64-channel block) and weight half-tiles (ring);
 //                              also allocates TMEM: 512 columns = 2 accumulator sets x R rows x 128 channels
 //   warp 15     MMA issuer     leader CTA only
-//   warps 4-11  epilogue       bias, skip, store, per-(pixel row, group) statistics of the stored values
-//   warps 0-3, 12, 13 transform  GroupNorm affine + SiLU in place on the halo (a pass-through when there is no norm)
+//   warps 8-13  transform      GroupNorm affine + SiLU in place on the halo (a pass-through when there is no norm)
+//   warps 0-7   epilogue       bias, skip, store, per-(pixel row, group) statistics of the stored values
 // The schedulers favour the highest warp id of their quarter, so the single-thread MMA issuer and the TMA producer sit
 // ABOVE every other warp: with the issuer as warp 1 the mere loop skeleton of a busy transform warp on the same
 // scheduler cost 25 % of the kernel's throughput (measured).
@@ -47,16 +47,16 @@ constexpr int CF_HW = CF_TW + 2;                       // halo width in pixels
 constexpr int CF_HR = CF_R + 2;                        // halo rows
 constexpr int CF_A_BYTES = CF_HR * CF_HW * 128;        // 66,560 (65 KB) per 64-channel block
 constexpr int CF_B_BYTES = (CF_BN / 2) * 64 * 2;       // 8 KB: this CTA's half of one tap's weight tile
-constexpr int CF_B_STAGES = 5;
+constexpr int CF_A_BUFS = 2;                            // halo buffers (a third one at the price of a 3-deep weight ring was measured: slower)
+constexpr int CF_B_STAGES = 10;                         // weight ring: 8 KB per stage; at 3 stages the kernel loses 20-40 %
 constexpr int CF_THREADS = 512;
-constexpr int CF_TWARPS = 6;                           // transform warps: 0-3, 12, 13
-constexpr int CF_TABLE_BYTES = 512 * 2 * 4;            // per-channel (scale, shift), Cin <= 512
+constexpr int CF_TWARPS = 6;                           // transform warps: 8-13
 constexpr int CF_STAT_BYTES = 2 * 8 * CF_R * 2 * 8 * 2 * 4;   // [parity][warp][row][chunk][group<=8][sum,sumsq]
-constexpr int CF_OFF_B = 2 * CF_A_BYTES;
-constexpr int CF_OFF_TABLE = CF_OFF_B + CF_B_STAGES * CF_B_BYTES;
-constexpr int CF_OFF_STAT = CF_OFF_TABLE + CF_TABLE_BYTES;
+constexpr int CF_OFF_B = CF_A_BUFS * CF_A_BYTES;
+constexpr int CF_OFF_STAT = CF_OFF_B + CF_B_STAGES * CF_B_BYTES;
 constexpr int CF_OFF_BAR = CF_OFF_STAT + CF_STAT_BYTES;
 constexpr int CF_SMEM_BYTES = CF_OFF_BAR + 256 + 1024;
+static_assert(CF_SMEM_BYTES <= 232448, "conv_fused: shared memory budget");
 
 struct ConvFParams {
   int B, H, W;          // grid of tile coordinates = the conv INPUT image (source image in upsample mode)
@@ -169,15 +169,14 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   using H16 = Half16<T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sA = smem;                       // [2][CF_A_BYTES]
+  uint8_t* sA = smem;                       // [CF_A_BUFS][CF_A_BYTES]
   uint8_t* sB = smem + CF_OFF_B;            // [CF_B_STAGES][CF_B_BYTES]
-  float* table = reinterpret_cast<float*>(smem + CF_OFF_TABLE);
   float* sstat = reinterpret_cast<float*>(smem + CF_OFF_STAT);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + CF_OFF_BAR);
-  uint64_t* a_land = bars;                  // [2] local: TMA halo landed in THIS CTA
-  uint64_t* a_ready = a_land + 2;           // [2] leader's copy live: both CTAs' halos transformed (8 warp arrivals)
-  uint64_t* a_empty = a_ready + 2;          // [2] multicast commit: the MMAs reading the buffer have retired
-  uint64_t* b_full = a_empty + 2;           // [CF_B_STAGES] leader's copy live (2 expect_tx arrivals)
+  uint64_t* a_land = bars;                  // [CF_A_BUFS] local: TMA halo landed in THIS CTA
+  uint64_t* a_ready = a_land + CF_A_BUFS;   // [CF_A_BUFS] leader's copy live: both CTAs' halos transformed
+  uint64_t* a_empty = a_ready + CF_A_BUFS;  // [CF_A_BUFS] multicast commit: the MMAs reading the buffer have retired
+  uint64_t* b_full = a_empty + CF_A_BUFS;   // [CF_B_STAGES] leader's copy live (2 expect_tx arrivals)
   uint64_t* b_empty = b_full + CF_B_STAGES; // [CF_B_STAGES] multicast commit
   uint64_t* tfull = b_empty + CF_B_STAGES;  // [2] multicast commit: accumulator set complete
   uint64_t* tempty = tfull + 2;             // [2] leader's copy live: 16 epilogue-warp arrivals
@@ -199,10 +198,12 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tma_prefetch_desc(&tmW);
   }
   if (warp == 15 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < CF_A_BUFS; ++i) {
       mbar_init(&a_land[i], 1);
       mbar_init(&a_ready[i], 2 * CF_TWARPS);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 16);
     }
@@ -239,7 +240,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tma_load_4d(sA + abuf * CF_A_BYTES, &tmX, &a_land[abuf], cb * 64, x0 - 1, y0 - 1, it.b);
         }
         __syncwarp();
-        if (++abuf == 2) {
+        if (++abuf == CF_A_BUFS) {
           abuf = 0;
           aph ^= 1;
         }
@@ -309,52 +310,52 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
               bph ^= 1;
             }
           }
-          if (++abuf == 2) {
+          if (++abuf == CF_A_BUFS) {
             abuf = 0;
             aph ^= 1;
           }
         }
       }
     }
-  } else if (warp < 4 || warp >= 12) {
+  } else if (warp >= 8) {
     // ------------------------------------------------------------------ transform warps: GroupNorm affine + SiLU in place
     // Six warps (192 threads); a thread owns one logical 16-byte chunk (8 channels) of every 24th halo pixel, two pixels
     // per iteration with both shared-memory loads issued first.  Budget per 64-channel block: the MMAs of the block take
     // 9 taps x 2 rows x 256 clk = 4608 clk; 33,280 halo elements need 2080 clk of MUFU.TANH (16 / clk / SM).
-    const int tw = warp >= 12 ? warp - 8 : warp;         // 0..5
+    const int tw = warp - 8;                              // 0..5
     const int tid = tw * 32 + lane;                       // 0..191
     constexpr int TT = CF_TWARPS * 32;
     const int chunk = tid & 7;                 // logical 16-byte chunk = 8 channels of the 64-channel block
     const int cpg = p.gn_stats != nullptr ? p.Cin / p.G : 1;
     uint32_t abuf = 0, aph = 0;
-    int cur_b = -1;
     for (int item = pair_id; item < total_items; item += num_pairs) {
       CfItem it;
       cf_decode(p, item, it);
       const int y0 = (it.ty * 2 + static_cast<int>(rank)) * CF_R;
       const int x0 = it.tx * CF_TW;
-      if (p.gn_stats != nullptr && it.b != cur_b) {
-        // per-channel (scale, shift) of this image: y = x * (rstd * gamma) + (beta - mean * rstd * gamma)
-        named_bar_sync(2, TT);                 // nobody still reads the previous image's table
-        for (int c = tid; c < p.Cin; c += TT) {
-          const int g = c / cpg;
-          const float mean = p.gn_stats[(it.b * p.G + g) * 2], rstd = p.gn_stats[(it.b * p.G + g) * 2 + 1];
-          const float ga = H16::to_f(reinterpret_cast<const T*>(p.gamma)[c]);
-          const float be = H16::to_f(reinterpret_cast<const T*>(p.beta)[c]);
-          table[2 * c] = rstd * ga;
-          table[2 * c + 1] = be - mean * rstd * ga;
-        }
-        named_bar_sync(2, TT);
-        cur_b = it.b;
-      }
       for (int cb = 0; cb < cblocks; ++cb) {
         mbar_wait(&a_land[abuf], aph);
         if (p.gn_stats != nullptr) {
+          // per-channel (scale, shift) of this image: y = x * (rstd * gamma) + (beta - mean * rstd * gamma); the 8
+          // channels of this thread's chunk come straight from global memory (a few hundred bytes per image, L1-resident)
           float sc[8], sh[8];
+          {
+            const int c0 = cb * 64 + chunk * 8;
+            const uint4 g4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.gamma) + c0);
+            const uint4 b4 = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.beta) + c0);
+            const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, bw[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            sc[j] = table[2 * (cb * 64 + chunk * 8 + j)];
-            sh[j] = table[2 * (cb * 64 + chunk * 8 + j) + 1];
+            for (int i = 0; i < 4; ++i) {
+              const float2 gf = H16::unpack(gw[i]), bf = H16::unpack(bw[i]);
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int g = (c0 + 2 * i + h2) / cpg;
+                const float mean = __ldg(p.gn_stats + (it.b * p.G + g) * 2), rstd = __ldg(p.gn_stats + (it.b * p.G + g) * 2 + 1);
+                const float ga = h2 ? gf.y : gf.x, be = h2 ? bf.y : bf.x;
+                sc[2 * i + h2] = rstd * ga;
+                sh[2 * i + h2] = be - mean * rstd * ga;
+              }
+            }
           }
           const uint32_t base = smem_u32(sA) + abuf * CF_A_BYTES;
           const bool do_silu = p.silu != 0;
@@ -399,16 +400,16 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&a_ready[abuf]), 0));
-        if (++abuf == 2) {
+        if (++abuf == CF_A_BUFS) {
           abuf = 0;
           aph ^= 1;
         }
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: this CTA's R x 128 output pixels
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 0-7): this CTA's R x 128 output pixels
     const int quarter = warp & 3;
-    const int half = (warp - 4) >> 2;           // 64-channel half of the 128-channel tile
+    const int half = warp >> 2;                 // 64-channel half of the 128-channel tile
     const int xl = quarter * 32 + lane;         // pixel inside the 128-pixel segment
     const T* bias = reinterpret_cast<const T*>(p.bias);
     const T* res = reinterpret_cast<const T*>(p.res);
@@ -427,7 +428,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int n_base = it.nt * CF_BN + half * 64;
       mbar_wait_warp(&tfull[acc], (n_it >> 1) & 1u);
       tc_fence_after();
-      float* st_my = sstat + (((n_it & 1u) * 8 + (warp - 4)) * CF_R) * (2 * 8 * 2);
+      float* st_my = sstat + (((n_it & 1u) * 8 + warp) * CF_R) * (2 * 8 * 2);
 #pragma unroll
       for (int rr = 0; rr < CF_R; ++rr) {
         const int oy = p.up ? 2 * (y0 + rr) + py : (y0 + rr);
@@ -499,7 +500,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         // segment and group
         named_bar_sync(1, 256);
         const int ng = 32 / cpg_out;
-        const int t = threadIdx.x - 128;        // 0..255
+        const int t = threadIdx.x;              // 0..255
         const int per_row = 2 * 2 * ng;         // halves x chunks x groups of this tile, per output row
         if (t < CF_R * per_row) {
           const int rr = t / per_row;

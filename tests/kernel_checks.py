@@ -430,6 +430,17 @@ def check_attention_v4_kernel():
     return out
 
 
+def check_attention_v3_explicit():
+    """v3 selected explicitly for both head dims (the default picks v5 for d = 64)"""
+    os.environ["DK_ATTENTION_IMPL"] = "3"
+    _setup()
+    out = {"d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att3_d64_S1178"),
+           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att3_d64_S333"),
+           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att3_d128_S300")}
+    out["rescale"] = check_attention_large_scores()["err"]
+    return out
+
+
 def check_attention_v5_kernel():
     """persistent kernel with register-resident scores and speculative exponentials (DK_ATTENTION_IMPL=5): one and many
     work items per CTA (items > SMs), odd/even K/V tile counts, tails, both head dims, split outputs, lazy rescale"""
@@ -1017,13 +1028,13 @@ ALL_CHECKS = [
     check_gemm_pair_kernel, check_gemm_pair_legacy_store, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
     check_text_kernels, check_attention_small,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
-    check_attention_v1_kernel, check_attention_v2_kernel, check_conv_fused,
+    check_attention_v1_kernel, check_attention_v2_kernel, check_attention_v3_explicit, check_attention_v5_kernel,
+    check_conv_fused,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,
 ] + FULLSIZE_CHECKS
 
 # kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
 # suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
-EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel,
-                       check_attention_v5_kernel]
+EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel]
 
