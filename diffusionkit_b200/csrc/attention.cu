@@ -48,7 +48,8 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
   uint64_t* s_full = v_empty + KS;         // [2]  QK_w(j) retired
   uint64_t* p_full = s_full + 2;           // [2]  softmax_w(j) published P_w(j) (128 arrivals)
   uint64_t* o_full = p_full + 2;           // [2]  PV_w(n-1) retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* p_half = o_full + 2;           // [2]  VAR 4: first 32 keys of every thread's P published (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_half + 2);
   float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_BAR + 256);   // [tile 2][half 2][row 128] partial max / sum
 
   const int warp = threadIdx.x >> 5;
@@ -73,6 +74,7 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 256);
       mbar_init(&o_full[i], 1);
+      mbar_init(&p_half[i], 256);
     }
     fence_barrier_init();
   }
@@ -155,6 +157,19 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
           umma_ts(d_tmem, p_tmem + (k >> 2) * 64 + (k & 3) * 8, smem_desc_join(v_lo + k * (2048 >> 4), desc_hi),
                   idesc_pv, (!first || k != 0) ? 1u : 0u);
       };
+      // VAR 4: the PV MMAs of the key slices whose P is published first (keys 0-31 and 64-95: the first 32 keys of both
+      // threads of every row) are issued while the exponentials of the other 32 keys are still running
+      auto issue_pv_part = [&](int w, int st, bool first, int part) {
+        const uint32_t v_lo = v_lo0 + st * TILE16;
+        const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + w * 128;
+        const uint32_t d_tmem = tmem_base + Cfg::TMEM_O + w * 128;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = (kk >> 1) * 4 + part * 2 + (kk & 1);   // part 0: 0, 1, 4, 5   part 1: 2, 3, 6, 7
+          umma_ts(d_tmem, p_tmem + (k >> 2) * 64 + (k & 3) * 8, smem_desc_join(v_lo + k * (2048 >> 4), desc_hi),
+                  idesc_pv, (!first || part != 0 || kk != 0) ? 1u : 0u);
+        }
+      };
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
@@ -166,6 +181,36 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
       __syncwarp();
       int st = 0;
       uint32_t par = 0;
+      if constexpr (VAR == 4) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st_n = (st + 1 == KS) ? 0 : st + 1;
+          const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
+          const bool more = j + 1 < n_tiles;
+          mbar_wait(&v_full[st], par);
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            mbar_wait(&p_half[w], j & 1);
+            tc_fence_after();
+            if (elect_one_sync()) issue_pv_part(w, st, j == 0, 0);
+            __syncwarp();
+            mbar_wait(&p_full[w], j & 1);
+            if (more && w == 0) mbar_wait(&k_full[st_n], par_n);
+            tc_fence_after();
+            if (elect_one_sync()) {
+              issue_pv_part(w, st, j == 0, 1);
+              if (w == 1) umma_commit(&v_empty[st]);
+              if (!more) umma_commit(&o_full[w]);
+              if (more) {
+                issue_qk(w, st_n);
+                if (w == 1) umma_commit(&k_empty[st_n]);
+              }
+            }
+            __syncwarp();
+          }
+          st = st_n;
+          par = par_n;
+        }
+      } else
       for (int j = 0; j < n_tiles; ++j) {
         const int st_n = (st + 1 == KS) ? 0 : st + 1;
         const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
@@ -175,19 +220,21 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
         if (more) mbar_wait(&k_full[st_n], par_n);
         tc_fence_after();
         if (elect_one_sync()) {
-          issue_pv(0, st, j == 0);
+          if (p.debug != 5) issue_pv(0, st, j == 0);
           if (!more) umma_commit(&o_full[0]);
-          if (more) issue_qk(0, st_n);
+          if (more && p.debug != 6) issue_qk(0, st_n);
+          if (more && p.debug == 6) umma_commit(&s_full[0]);
         }
         __syncwarp();
         if (p.debug < 4) mbar_wait(&p_full[1], j & 1);
         tc_fence_after();
         if (elect_one_sync()) {
-          issue_pv(1, st, j == 0);
+          if (p.debug != 5) issue_pv(1, st, j == 0);
           umma_commit(&v_empty[st]);
           if (!more) umma_commit(&o_full[1]);
           if (more) {
-            issue_qk(1, st_n);
+            if (p.debug != 6) issue_qk(1, st_n);
+            if (p.debug == 6) umma_commit(&s_full[1]);
             umma_commit(&k_empty[st_n]);
           }
         }
@@ -364,6 +411,11 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
             pk[i] = H16::pack(e0, e1);
           }
           tmem_st_32x16(t_s + c * 16, pk);
+          if (VAR == 4 && c == 0) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_half[w]);
+          }
         }
       } else {
 #pragma unroll 1
@@ -384,6 +436,11 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
             pk[i] = H16::pack(e0, e1);
           }
           tmem_st_32x16(t_s + c * 16, pk);
+          if (VAR == 4 && c == 0) {
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&p_half[w]);
+          }
         }
       }
       l_run += ls0 + ls1;
@@ -396,7 +453,7 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
     mbar_wait(&o_full[w], 0);
     tc_fence_after();
     *my_x = l_run;
-    if constexpr (VAR >= 1)
+    if constexpr (VAR == 1 || VAR == 2)
       named_bar_sync(1 + w * 4 + quarter, 64);
     else
       named_bar_sync(1 + w, 256);
@@ -486,20 +543,31 @@ static int launch_attention_v3p(dk_ctx* ctx, const CUtensorMap& tm, const AttPar
 }
 template <typename T, int D>
 static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
-  static const int poly = [] {
+  // Tuning knobs (defaults = the best same-box A/B of round 2, profiles/r02_att_ab*.txt):
+  //   DK_ATT_SPLIT (default 1): publish P in two halves so that the PV MMAs of the first 32 keys of every thread are
+  //                 issued while the exponentials of the other 32 are still running (+4.7 % at d = 128)
+  //   DK_ATT_POLY  (default 0 for d = 128, 1 for d = 64): of every four exponentials, how many run as a cubic on the
+  //                 FMA pipe instead of MUFU.EX2 (d = 64 is MUFU-bound 2:1: 568 -> 671 TFLOP/s with split + poly 1;
+  //                 d = 128: 1133 -> 1194 with the split alone, poly costs 1-3 % there)
+  static const int poly_env = [] {
     const char* e = getenv("DK_ATT_POLY");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : -1;
   }();
-  static const bool var1 = [] {
-    const char* e = getenv("DK_ATTENTION_IMPL");
-    return e != nullptr && e[0] == '3' && e[1] == 'b';
+  static const int split_env = [] {
+    const char* e = getenv("DK_ATT_SPLIT");
+    return e ? atoi(e) : -1;
   }();
-  if (var1) return launch_attention_v3p<T, D, 0, 1>(ctx, tm, p, stream);
-  static const bool var2 = [] {
-    const char* e = getenv("DK_ATTENTION_IMPL");
-    return e != nullptr && e[0] == '3' && e[1] == 'r';
-  }();
-  if (var2) return launch_attention_v3r<T, D>(ctx, tm, p, stream);
+  static const char* impl = getenv("DK_ATTENTION_IMPL");
+  if (impl != nullptr && impl[0] == '3' && impl[1] == 'b') return launch_attention_v3p<T, D, 0, 1>(ctx, tm, p, stream);
+  if (impl != nullptr && impl[0] == '3' && impl[1] == 'r') return launch_attention_v3r<T, D>(ctx, tm, p, stream);
+  const bool plain = impl != nullptr && impl[0] == '3' && impl[1] == 'p';   // round-1 behaviour: no split, no poly
+  const bool split = !plain && (split_env >= 0 ? split_env != 0 : true);
+  const int poly = plain ? 0 : (poly_env >= 0 ? poly_env : (D == 64 ? 1 : 0));
+  if (split) {
+    if (poly <= 0) return launch_attention_v3p<T, D, 0, 4>(ctx, tm, p, stream);
+    if (poly == 1) return launch_attention_v3p<T, D, 1, 4>(ctx, tm, p, stream);
+    return launch_attention_v3p<T, D, 2, 4>(ctx, tm, p, stream);
+  }
   if (poly <= 0) return launch_attention_v3p<T, D, 0>(ctx, tm, p, stream);
   if (poly == 1) return launch_attention_v3p<T, D, 1>(ctx, tm, p, stream);
   return launch_attention_v3p<T, D, 2>(ctx, tm, p, stream);
@@ -563,9 +631,7 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
     const char* e = getenv("DK_ATTENTION_IMPL");
     return e != nullptr && e[0] == '5';
   }();
-  // default per head dim (same-box A/B, round 2): d = 64 (SD3) -> v5, 646 vs 570 TFLOP/s; d = 128 (FLUX) -> v3, 1133 vs 1121
-  static const bool impl_unset = getenv("DK_ATTENTION_IMPL") == nullptr;
-  if (use_v5 || (impl_unset && d == 64)) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
+  if (use_v5) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
   if (legacy_impl != 0) return dk_launch_attention_legacy(ctx, legacy_impl, dtype, d, tm, p, stream);
   if (dtype == DK_BF16) {
     if (d == 128) return launch_attention_v3<__nv_bfloat16, 128>(ctx, tm, p, stream);

@@ -28,8 +28,10 @@
 //   warp 14     TMA producer   halo boxes (double buffered per 64-channel block) and weight half-tiles (ring);
 //                              also allocates TMEM: 512 columns = 2 accumulator sets x R rows x 128 channels
 //   warp 15     MMA issuer     leader CTA only
-//   warps 8-13  transform      GroupNorm affine + SiLU in place on the halo (a pass-through when there is no norm)
-//   warps 0-7   epilogue       bias, skip, store, per-(pixel row, group) statistics of the stored values
+//   warps 4-11  epilogue       bias, skip, store, per-(pixel row, group) statistics of the stored values
+//   warps 0-3, 12, 13 transform  GroupNorm affine + SiLU in place on the halo (a pass-through when there is no norm);
+//               (measured against transform = warps 8-13 above an epilogue on warps 0-7: 1.22 vs 1.54 ms on the
+//               1024^2 x 128 norm+SiLU layer)
 // The schedulers favour the highest warp id of their quarter, so the single-thread MMA issuer and the TMA producer sit
 // ABOVE every other warp: with the issuer as warp 1 the mere loop skeleton of a busy transform warp on the same
 // scheduler cost 25 % of the kernel's throughput (measured).
@@ -50,7 +52,7 @@ constexpr int CF_B_BYTES = (CF_BN / 2) * 64 * 2;       // 8 KB: this CTA's half 
 constexpr int CF_A_BUFS = 2;                            // halo buffers (a third one at the price of a 3-deep weight ring was measured: slower)
 constexpr int CF_B_STAGES = 10;                         // weight ring: 8 KB per stage; at 3 stages the kernel loses 20-40 %
 constexpr int CF_THREADS = 512;
-constexpr int CF_TWARPS = 6;                           // transform warps: 8-13
+constexpr int CF_TWARPS = 6;                           // transform warps: 0-3, 12, 13
 constexpr int CF_STAT_BYTES = 2 * 8 * CF_R * 2 * 8 * 2 * 4;   // [parity][warp][row][chunk][group<=8][sum,sumsq]
 constexpr int CF_OFF_B = CF_A_BUFS * CF_A_BYTES;
 constexpr int CF_OFF_STAT = CF_OFF_B + CF_B_STAGES * CF_B_BYTES;
@@ -317,12 +319,12 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp < 4 || warp >= 12) {
     // ------------------------------------------------------------------ transform warps: GroupNorm affine + SiLU in place
     // Six warps (192 threads); a thread owns one logical 16-byte chunk (8 channels) of every 24th halo pixel, two pixels
     // per iteration with both shared-memory loads issued first.  Budget per 64-channel block: the MMAs of the block take
     // 9 taps x 2 rows x 256 clk = 4608 clk; 33,280 halo elements need 2080 clk of MUFU.TANH (16 / clk / SM).
-    const int tw = warp - 8;                              // 0..5
+    const int tw = warp >= 12 ? warp - 8 : warp;         // 0..5
     const int tid = tw * 32 + lane;                       // 0..191
     constexpr int TT = CF_TWARPS * 32;
     const int chunk = tid & 7;                 // logical 16-byte chunk = 8 channels of the 64-channel block
@@ -407,9 +409,9 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 0-7): this CTA's R x 128 output pixels
+    // ------------------------------------------------------------------ epilogue (warps 4-11): this CTA's R x 128 output pixels
     const int quarter = warp & 3;
-    const int half = warp >> 2;                 // 64-channel half of the 128-channel tile
+    const int half = (warp - 4) >> 2;           // 64-channel half of the 128-channel tile
     const int xl = quarter * 32 + lane;         // pixel inside the 128-pixel segment
     const T* bias = reinterpret_cast<const T*>(p.bias);
     const T* res = reinterpret_cast<const T*>(p.res);
@@ -428,7 +430,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int n_base = it.nt * CF_BN + half * 64;
       mbar_wait_warp(&tfull[acc], (n_it >> 1) & 1u);
       tc_fence_after();
-      float* st_my = sstat + (((n_it & 1u) * 8 + warp) * CF_R) * (2 * 8 * 2);
+      float* st_my = sstat + (((n_it & 1u) * 8 + (warp - 4)) * CF_R) * (2 * 8 * 2);
 #pragma unroll
       for (int rr = 0; rr < CF_R; ++rr) {
         const int oy = p.up ? 2 * (y0 + rr) + py : (y0 + rr);
@@ -500,7 +502,7 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         // segment and group
         named_bar_sync(1, 256);
         const int ng = 32 / cpg_out;
-        const int t = threadIdx.x;              // 0..255
+        const int t = threadIdx.x - 128;        // 0..255
         const int per_row = 2 * 2 * ng;         // halves x chunks x groups of this tile, per output row
         if (t < CF_R * per_row) {
           const int rr = t / per_row;

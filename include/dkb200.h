@@ -17,6 +17,21 @@
  *     activations; sampler state is fp32 (__init__.py:761-788).
  *   - layouts follow the reference: latents/images NHWC (mmdit.py:188-266, vae.py:386-401),
  *     Linear weights (out,in) (mlx nn.Linear), conv weights (O,kh,kw,I) (mlx nn.Conv2d).
+ *
+ * Why the boundary is at the OPERATOR level (and not dk_mmdit_forward / dk_vae_decode)
+ *   The reference's own boundary to its accelerator library is the operator level: mmdit.py / vae.py are
+ *   Python modules that call mx.fast.scaled_dot_product_attention, mx.fast.layer_norm, nn.Linear,
+ *   nn.Conv2d, nn.GroupNorm one by one; model structure (block lists, which stream skips its post-attention
+ *   path, the modulation cache keyed by timestep, the img2img branch) lives in Python and is what its
+ *   maintainers edit.  This header replaces exactly that layer — every MLX call on the path has one entry
+ *   point here, with the fusions expressed as epilogue/prologue arguments of those calls — so a binding keeps
+ *   the reference's module code and swaps its library calls.  A model-level entry point would have to freeze
+ *   the parameter-tree naming, six model configurations, the modulation cache and the quirk flags of
+ *   SURVEY.md App. A.4 into a C struct.  The cost of staying at the operator level is launch overhead, which
+ *   the host layer removes by capturing each forward / decode in a CUDA graph (one cudaGraphLaunch per
+ *   MMDiT forward or VAE decode: diffusionkit_b200/mmdit.py, vae.py); a non-Python host does the same with
+ *   cudaStreamBeginCapture around its own sequence of dk_* calls — every entry point is capture-safe (no
+ *   allocation, no synchronisation, no host-side state beyond the launch counter).
  */
 #ifndef DKB200_H
 #define DKB200_H

@@ -431,12 +431,28 @@ def check_attention_v4_kernel():
 
 
 def check_attention_v3_explicit():
-    """v3 selected explicitly for both head dims (the default picks v5 for d = 64)"""
-    os.environ["DK_ATTENTION_IMPL"] = "3"
+    """the round-1 form of v3 (DK_ATTENTION_IMPL=3p: one P publication per step, every exponential on MUFU)"""
+    os.environ["DK_ATTENTION_IMPL"] = "3p"
     _setup()
     out = {"d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att3_d64_S1178"),
            "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att3_d64_S333"),
            "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att3_d128_S300")}
+    out["rescale"] = check_attention_large_scores()["err"]
+    return out
+
+
+def check_attention_v3s_kernel():
+    """v3 with the split P publication (DK_ATTENTION_IMPL=3s): the PV MMAs of the first 32 keys of every thread are issued
+    while the exponentials of the other 32 are still running"""
+    os.environ["DK_ATTENTION_IMPL"] = "3"
+    os.environ["DK_ATT_SPLIT"] = "1"
+    os.environ["DK_ATT_POLY"] = "1"
+    _setup()
+    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att3s_d128_S128"),
+           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att3s_d128_S300"),
+           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att3s_d128_S1280"),
+           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att3s_d64_S1178"),
+           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att3s_S1")}
     out["rescale"] = check_attention_large_scores()["err"]
     return out
 
@@ -1036,5 +1052,5 @@ ALL_CHECKS = [
 
 # kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
 # suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
-EXPERIMENTAL_CHECKS = [check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel]
+EXPERIMENTAL_CHECKS = [check_attention_v3s_kernel, check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel]
 
