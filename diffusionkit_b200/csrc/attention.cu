@@ -4,7 +4,8 @@
 // non-causal, joint [text|image] sequence, head dim 64 (SD3) or 128 (FLUX).
 //
 // This file: the current kernel (v3: two 128-row Q tiles per CTA, two softmax warpgroups per tile, P kept in TMEM) and
-// the C entry point; the earlier generations live in attention_legacy.cu.
+// the C entry point.  (The earlier generations — P through shared memory, one softmax warpgroup per tile — and the
+// variants measured and rejected in round 2 are in the git history; DESIGN.md lists what each taught.)
 #include "attention.cuh"
 
 namespace dk {
@@ -23,12 +24,7 @@ namespace dk {
 constexpr int ATT3_THREADS = 576;
 
 // POLY4: of every four exponentials, how many run on the FMA pipe (ex2_poly) instead of MUFU.EX2 (0, 1 or 2)
-// VAR 1 (DK_ATTENTION_IMPL=3b, experimental, not yet measured): shorter non-exponential phases of the softmax leg —
-// the two threads that share a row synchronise through a 64-thread named barrier of their own (one per TMEM lane quarter
-// and Q tile) instead of the tile-wide 256-thread one, and the row max runs as four independent chains.  Same
-// arithmetic as VAR 0 (max is exact).  Tried at compile time and dropped: keeping the 64 scores in registers between
-// the two passes, or issuing the second pass's first TMEM read before the exchange — both need > 96 registers at this
-// CTA size (130-140 bytes of spills).
+// VAR 4: split P publication (see launch_attention_v3); VAR 0: one publication per step.
 template <typename T, int D, int POLY4, int VAR>
 __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, const AttParams& p) {
   using H16 = Half16<T>;
@@ -264,71 +260,6 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
       const int kv_valid = p.S - j * ATT_BKV - hh * 64;   // valid keys in this half (tail tile only matters)
-      if constexpr (VAR == 2) {
-        // register-resident variant (attention_fwd_v3r_kernel, 112 registers): ONE TMEM read per step — the 64 scores
-        // stay in registers from the max pass to the exponentials; pairwise barrier and 4 max chains as in VAR 1
-        uint32_t sr[2][32];
-        tmem_ld_32x32(t_s, sr[0]);
-        tmem_ld_32x32(t_s + 32, sr[1]);
-        tmem_ld_wait();
-        if (kv_valid < 64) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
-        }
-        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          m4[0] = fmaxf(m4[0], __uint_as_float(sr[0][i]));
-          m4[1] = fmaxf(m4[1], __uint_as_float(sr[0][16 + i]));
-          m4[2] = fmaxf(m4[2], __uint_as_float(sr[1][i]));
-          m4[3] = fmaxf(m4[3], __uint_as_float(sr[1][16 + i]));
-        }
-        const float mx_h = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        *my_x = mx_h;
-        named_bar_sync(1 + w * 4 + quarter, 64);
-        const float mx2 = fmaxf(mx_h, *peer_x) * sl2;
-        const float m_new2 = fmaxf(m_run, mx2);
-        const bool need2 = (m_new2 - m_run) > 8.0f;
-        if (__any_sync(0xffffffffu, need2)) {
-          const float alpha = ex2_approx(m_run - m_new2);
-          m_run = m_new2;
-          l_run *= alpha;
-          if (j > 0) {   // rare path: 16 columns at a time, the 64 scores stay in registers meanwhile
-#pragma unroll 1
-            for (int c = 0; c < OC / 16; ++c) {
-              uint32_t o[16];
-              tmem_ld_32x16(t_o + c * 16, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_32x16(t_o + c * 16, o);
-            }
-          }
-        }
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x0 = fmaf(__uint_as_float(sr[c][2 * i]), sl2, -m_run);
-            const float x1 = fmaf(__uint_as_float(sr[c][2 * i + 1]), sl2, -m_run);
-            const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-            s0 += e0;
-            s1 += e1;
-            pk[i] = H16::pack(e0, e1);
-          }
-          tmem_st_32x16(t_s + c * 16, pk);
-        }
-        l_run += s0 + s1;
-        tmem_st_wait();
-        tc_fence_before();
-        mbar_arrive(&p_full[w]);
-        continue;
-      }
       // pass 1: partial row max over this half's 64 scores
       float mx_half;
       {
@@ -343,18 +274,7 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;  // -inf
         }
-        if constexpr (VAR == 1) {
-          // four independent max chains of 16 instead of two of 32 (max is exact: same result)
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            m4[0] = fmaxf(m4[0], __uint_as_float(sr[0][i]));
-            m4[1] = fmaxf(m4[1], __uint_as_float(sr[0][16 + i]));
-            m4[2] = fmaxf(m4[2], __uint_as_float(sr[1][i]));
-            m4[3] = fmaxf(m4[3], __uint_as_float(sr[1][16 + i]));
-          }
-          mx_half = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        } else {
+        {
           float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -365,10 +285,7 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
         }
       }
       *my_x = mx_half;
-      if constexpr (VAR == 1)
-        named_bar_sync(1 + w * 4 + quarter, 64);   // just the two warps that share these 32 rows
-      else
-        named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible
+      named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible
       const float mx = fmaxf(mx_half, *peer_x) * sl2;
       const float m_new = fmaxf(m_run, mx);
       const bool need = (m_new - m_run) > 8.0f;   // identical in both halves (same inputs)
@@ -453,10 +370,7 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
     mbar_wait(&o_full[w], 0);
     tc_fence_after();
     *my_x = l_run;
-    if constexpr (VAR == 1 || VAR == 2)
-      named_bar_sync(1 + w * 4 + quarter, 64);
-    else
-      named_bar_sync(1 + w, 256);
+    named_bar_sync(1 + w, 256);
     const float inv_l = 1.0f / (l_run + *peer_x);
     const int s_idx = q0 + w * ATT_BQ + r;
     const bool row_ok = s_idx < p.S;
@@ -502,30 +416,6 @@ attention_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttPara
   attention_v3_body<T, D, POLY4, VAR>(tmQKV, p);
 }
 
-// VAR 2 under a register budget of 112 (576 x 112 = 64512 of the SM's 65536): __launch_bounds__(576) makes ptxas round
-// the CTA up to 640 threads and cap at 96.  DK_ATTENTION_IMPL=3r, experimental, not yet measured.
-template <typename T, int D>
-__global__ void __maxnreg__(112)
-attention_fwd_v3r_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttParams p) {
-  attention_v3_body<T, D, 0, 2>(tmQKV, p);
-}
-
-template <typename T, int D>
-static int launch_attention_v3r(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
-  using Cfg = Att2Cfg<D>;
-  constexpr int SMEM = Cfg::SMEM_BYTES + 2 * 2 * 128 * 4;
-  auto kern = attention_fwd_v3r_kernel<T, D>;
-  static bool configured = false;
-  if (!configured) {
-    DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
-  dim3 grid(dk_ceil_div(p.S, 2 * ATT_BQ), p.heads, p.B);
-  kern<<<grid, ATT3_THREADS, SMEM, stream>>>(tm, p);
-  DK_LAUNCH_CHECK(ctx);
-  return 0;
-}
-
 template <typename T, int D, int POLY4, int VAR = 0>
 static int launch_attention_v3p(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
   using Cfg = Att2Cfg<D>;
@@ -558,8 +448,6 @@ static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttPara
     return e ? atoi(e) : -1;
   }();
   static const char* impl = getenv("DK_ATTENTION_IMPL");
-  if (impl != nullptr && impl[0] == '3' && impl[1] == 'b') return launch_attention_v3p<T, D, 0, 1>(ctx, tm, p, stream);
-  if (impl != nullptr && impl[0] == '3' && impl[1] == 'r') return launch_attention_v3r<T, D>(ctx, tm, p, stream);
   const bool plain = impl != nullptr && impl[0] == '3' && impl[1] == 'p';   // round-1 behaviour: no split, no poly
   const bool split = !plain && (split_env >= 0 ? split_env != 0 : true);
   const int poly = plain ? 0 : (poly_env >= 0 ? poly_env : (D == 64 ? 1 : 0));
@@ -612,27 +500,13 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
   p.ld0 = ld0;
   p.out1 = out1;
   p.ld1 = ld1;
-  // default: v3 (same-box A/B at the C4 shape: v3 1120, v2 1058, v2a 1064 TFLOP/s).  DK_ATTENTION_IMPL=3b / 3r select its
-  // experimental variants, 2 / 2a / 1 the older kernels of attention_legacy.cu;
-  // DK_ATT_POLY (0..2, default 0): share of the softmax exponentials evaluated on the FMA pipe (tuning knob)
-  static const int legacy_impl = [] {
-    const char* e = getenv("DK_ATTENTION_IMPL");
-    if (e == nullptr || e[0] == '3' || e[0] == '4' || e[0] == '5') return 0;
-    if (e[0] == '2' && e[1] == 'a') return 3;
-    if (e[0] == '1') return 1;
-    return 2;
-  }();
-  static const bool use_v4 = [] {
-    const char* e = getenv("DK_ATTENTION_IMPL");
-    return e != nullptr && e[0] == '4';
-  }();
-  if (use_v4) return dk_launch_attention_v4(ctx, dtype, d, tm, p, stream);   // experimental, attention_v4.cu
+  // default: v3 with the split P publication (launch_attention_v3); DK_ATTENTION_IMPL=5 selects the persistent
+  // single-pass kernel of attention_v5.cu, 3p the round-1 form of v3
   static const bool use_v5 = [] {
     const char* e = getenv("DK_ATTENTION_IMPL");
     return e != nullptr && e[0] == '5';
   }();
   if (use_v5) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
-  if (legacy_impl != 0) return dk_launch_attention_legacy(ctx, legacy_impl, dtype, d, tm, p, stream);
   if (dtype == DK_BF16) {
     if (d == 128) return launch_attention_v3<__nv_bfloat16, 128>(ctx, tm, p, stream);
     return launch_attention_v3<__nv_bfloat16, 64>(ctx, tm, p, stream);

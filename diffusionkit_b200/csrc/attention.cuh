@@ -1,5 +1,4 @@
-// Shared definitions of the attention kernels (attention.cu: the current kernel; attention_legacy.cu: the earlier
-// generations kept selectable for same-box A/B measurements).
+// Shared definitions of the attention kernels (attention.cu: v3, the default; attention_v5.cu: the persistent variant).
 #pragma once
 
 #include <stdlib.h>
@@ -38,16 +37,6 @@ struct Att2Cfg {
 };
 
 }  // namespace dk
-
-// Older kernels (attention_legacy.cu).  impl: 1 = one Q tile per CTA, P through shared memory; 2 = two Q tiles, one
-// softmax warpgroup each, P in TMEM; 3 ("2a") = the first version of 2.
-int dk_launch_attention_legacy(dk_ctx* ctx, int impl, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
-                               cudaStream_t stream);
-
-// EXPERIMENTAL one-Q-tile kernel with a double-buffered score accumulator (attention_v4.cu, DK_ATTENTION_IMPL=4)
-int dk_launch_attention_v4(dk_ctx* ctx, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
-                           cudaStream_t stream);
-
 
 // v5 (attention_v5.cu, DK_ATTENTION_IMPL=5): persistent CTAs, register-resident scores, speculative exponentials
 int dk_launch_attention_v5(dk_ctx* ctx, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,

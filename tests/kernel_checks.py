@@ -365,71 +365,6 @@ def check_attention_d64():
     return out
 
 
-def check_attention_v1_kernel():
-    """the single-Q-tile kernel with P staged through shared memory (DK_ATTENTION_IMPL=1) stays correct"""
-    os.environ["DK_ATTENTION_IMPL"] = "1"
-    _setup()
-    return {"d128": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att_v1_d128"),
-            "d64": _attention_case(1, 1178, 2, 64, torch.float16, split=1024, name="att_v1_d64")}
-
-
-def check_attention_v2_kernel():
-    """the one-softmax-warpgroup-per-Q-tile kernel (DK_ATTENTION_IMPL=2) stays correct; the default is v3"""
-    os.environ["DK_ATTENTION_IMPL"] = "2"
-    _setup()
-    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att2_d128_S128"),
-           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att2_d128_S300"),
-           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att2_d128_S1280"),
-           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att2_d64_S1178"),
-           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att2_d64_S333"),
-           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att2_S1")}
-    out["rescale"] = check_attention_large_scores()["err"]
-    return out
-
-
-def check_attention_v3b_kernel():
-    """v3 with pairwise 64-thread barriers between the two halves of a row (DK_ATTENTION_IMPL=3b, experimental):
-    same arithmetic as the default kernel"""
-    os.environ["DK_ATTENTION_IMPL"] = "3b"
-    _setup()
-    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att3b_d128_S128"),
-           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att3b_d128_S300"),
-           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att3b_d128_S1280"),
-           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att3b_d64_S1178"),
-           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att3b_S1")}
-    out["rescale"] = check_attention_large_scores()["err"]
-    return out
-
-
-def check_attention_v3r_kernel():
-    """v3 with register-resident scores (one TMEM read per step, 112 registers; DK_ATTENTION_IMPL=3r, experimental)"""
-    os.environ["DK_ATTENTION_IMPL"] = "3r"
-    _setup()
-    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att3r_d128_S128"),
-           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att3r_d128_S300"),
-           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att3r_d128_S1280"),
-           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att3r_d64_S1178"),
-           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att3r_S1")}
-    out["rescale"] = check_attention_large_scores()["err"]
-    return out
-
-
-def check_attention_v4_kernel():
-    """one Q tile per CTA, double-buffered scores, two alternating softmax sets (DK_ATTENTION_IMPL=4, experimental):
-    odd / even numbers of K/V tiles, a single tile, tails, both head dims, split outputs, the lazy-rescale path"""
-    os.environ["DK_ATTENTION_IMPL"] = "4"
-    _setup()
-    out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att4_d128_S128"),
-           "d128_S256": _attention_case(1, 256, 2, 128, torch.bfloat16, name="att4_d128_S256"),
-           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att4_d128_S300"),
-           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att4_d128_S1280"),
-           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att4_d64_S1178"),
-           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att4_d64_S333"),
-           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att4_S1")}
-    out["rescale"] = check_attention_large_scores()["err"]
-    return out
-
-
 def check_attention_v3_explicit():
     """the round-1 form of v3 (DK_ATTENTION_IMPL=3p: one P publication per step, every exponential on MUFU)"""
     os.environ["DK_ATTENTION_IMPL"] = "3p"
@@ -1044,7 +979,7 @@ ALL_CHECKS = [
     check_gemm_pair_kernel, check_gemm_pair_legacy_store, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
     check_text_kernels, check_attention_small,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
-    check_attention_v1_kernel, check_attention_v2_kernel, check_attention_v3_explicit, check_attention_v5_kernel,
+    check_attention_v3_explicit, check_attention_v3s_kernel, check_attention_v5_kernel,
     check_conv_fused,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,
@@ -1052,5 +987,5 @@ ALL_CHECKS = [
 
 # kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
 # suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
-EXPERIMENTAL_CHECKS = [check_attention_v3s_kernel, check_attention_v3b_kernel, check_attention_v3r_kernel, check_attention_v4_kernel]
+EXPERIMENTAL_CHECKS = []
 

@@ -292,14 +292,3 @@ def test_integration_doc_struct_is_current():
         names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", first.strip())[0])
         names += [r.strip().lstrip("*").strip() for r in rest]
     assert names == [n for n, _ in _lib.GemmArgs._fields_], (names, [n for n, _ in _lib.GemmArgs._fields_])
-
-
-def test_attention_v4_protocol_model():
-    """csrc/attention_v4.cu (experimental, one Q tile per CTA with a double-buffered score accumulator) has its barrier
-    protocol and arithmetic mirrored in tools/sim_attention_v4.py; under random interleavings it must neither deadlock
-    nor touch a buffer in the wrong state, and must reproduce softmax attention (this model caught two protocol bugs
-    before the kernel ever ran)"""
-    sys.path.insert(0, os.path.join(ROOT, "tools"))
-    import sim_attention_v4 as sim
-
-    assert sim.main(seeds=8) < 1e-9
