@@ -53,6 +53,7 @@ SIGNATURES = {
     "dk_ln_modulate": (i32, [vp, i32, vp, vp, vp, vp, i64, i32, i32, i32, f32, vp]),
     "dk_qk_norm_rope": (i32, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp]),
     "dk_attention_fwd": (i32, [vp, i32, vp, i32, i32, i32, i32, f32, i32, vp, i64, vp, i64, vp]),
+    "dk_attention_tuning": (i32, [i32, i32, i32]),
     "dk_silu_add": (i32, [vp, i32, vp, vp, vp, i32, i32, i32, vp]),
     "dk_act": (i32, [vp, i32, vp, vp, i64, i32, vp]),
     "dk_patchify": (i32, [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -24,7 +24,10 @@ namespace dk {
 constexpr int ATT3_THREADS = 576;
 
 // POLY4: of every four exponentials, how many run on the FMA pipe (ex2_poly) instead of MUFU.EX2 (0, 1 or 2)
-// VAR 4: split P publication (see launch_attention_v3); VAR 0: one publication per step.
+// VAR bits: 4 = split P publication (see launch_attention_v3); 32 = streamed exponential pass: the 64 scores of a
+// thread go through two 16-column register buffers, the next TMEM read in flight behind the current chunk and the TMEM
+// stores waited for only at the two publications, instead of two load -> wait -> compute -> store -> wait rounds;
+// 16 = diagnostic instantiation that records SM-clock timestamps of every hand-over (DK_ATT_TRACE).
 template <typename T, int D, int POLY4, int VAR>
 __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, const AttParams& p) {
   using H16 = Half16<T>;
@@ -82,6 +85,17 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // VAR bit 16 (diagnostic instantiation only): SM-clock timestamps of one CTA's hand-overs, step by step
+  //   trace[step][slot]: slots 0-19 softmax group g = 2*w + hh (5 each: S ready, max pass done, partner max read,
+  //   first half of P published, P published), 20-27 MMA issuer (4 per tile: first-half P seen, PV part 0 issued,
+  //   P seen, PV part 1 + next QK^T issued), 28 = K/V stage loaded (producer)
+  constexpr int TRACE_STEPS = 34, TRACE_SLOTS = 32;
+  const bool trace_cta = (VAR & 16) && p.trace != nullptr && blockIdx.x == 3 && blockIdx.y == 1 && blockIdx.z == 0;
+  auto stamp = [&](int step, int slot) {
+    if constexpr ((VAR & 16) != 0) {
+      if (trace_cta && step < TRACE_STEPS) p.trace[step * TRACE_SLOTS + slot] = clock64();
+    }
+  };
 
   if (warp >= 16) {
     if (warp == 16) {
@@ -177,7 +191,7 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
       __syncwarp();
       int st = 0;
       uint32_t par = 0;
-      if constexpr (VAR == 4) {
+      if constexpr ((VAR & 4) != 0) {
         for (int j = 0; j < n_tiles; ++j) {
           const int st_n = (st + 1 == KS) ? 0 : st + 1;
           const uint32_t par_n = (st + 1 == KS) ? (par ^ 1) : par;
@@ -187,11 +201,14 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
           for (int w = 0; w < 2; ++w) {
             mbar_wait(&p_half[w], j & 1);
             tc_fence_after();
+            if (lane == 0) stamp(j, 20 + 4 * w);
             if (elect_one_sync()) issue_pv_part(w, st, j == 0, 0);
             __syncwarp();
+            if (lane == 0) stamp(j, 21 + 4 * w);
             mbar_wait(&p_full[w], j & 1);
             if (more && w == 0) mbar_wait(&k_full[st_n], par_n);
             tc_fence_after();
+            if (lane == 0) stamp(j, 22 + 4 * w);
             if (elect_one_sync()) {
               issue_pv_part(w, st, j == 0, 1);
               if (w == 1) umma_commit(&v_empty[st]);
@@ -202,6 +219,7 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
               }
             }
             __syncwarp();
+            if (lane == 0) stamp(j, 23 + 4 * w);
           }
           st = st_n;
           par = par_n;
@@ -255,15 +273,23 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
     float m_run = -INFINITY;
     float l_run = 0.f;
     const float sl2 = p.scale_log2;
+    // publication of this thread's P columns: TMEM stores complete -> ordered before the arrive -> arrive
+    auto publish = [&](uint64_t* bar) {
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(bar);
+    };
 
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[w], j & 1);
       tc_fence_after();
+      const bool tr = quarter == 0 && lane == 0;
+      if (tr) stamp(j, 5 * g + 0);
       const int kv_valid = p.S - j * ATT_BKV - hh * 64;   // valid keys in this half (tail tile only matters)
       // pass 1: partial row max over this half's 64 scores
       float mx_half;
+      uint32_t sr[2][32];
       {
-        uint32_t sr[2][32];
         tmem_ld_32x32(t_s, sr[0]);
         tmem_ld_32x32(t_s + 32, sr[1]);
         tmem_ld_wait();
@@ -284,9 +310,11 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
           mx_half = fmaxf(mx0, mx1);
         }
       }
+      if (tr) stamp(j, 5 * g + 1);
       *my_x = mx_half;
       named_bar_sync(1 + w, 256);   // both halves of tile w: partial maxima visible
       const float mx = fmaxf(mx_half, *peer_x) * sl2;
+      if (tr) stamp(j, 5 * g + 2);
       const float m_new = fmaxf(m_run, mx);
       const bool need = (m_new - m_run) > 8.0f;   // identical in both halves (same inputs)
       if (__any_sync(0xffffffffu, need)) {
@@ -310,7 +338,42 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
       // (the tail mask lives in a branch of its own: as a per-element select inside the main loop it was 26 % of all
       //  instructions the kernel issued — ncu, ISETP + FSEL — on every step of every tile)
       float ls0 = 0.f, ls1 = 0.f;
-      if (kv_valid >= 64) {
+      if ((VAR & 32) && kv_valid >= 64) {
+        uint32_t sa[16], sb[16], pk[8];
+        // 16 scores -> 8 packed P columns (same element order, poly pattern and summation order as the plain form)
+        auto chunk = [&](const uint32_t (&sc)[16]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float x0 = fmaf(__uint_as_float(sc[2 * i]), sl2, -m_run);
+            const float x1 = fmaf(__uint_as_float(sc[2 * i + 1]), sl2, -m_run);
+            const float e0 = ex2_approx(x0);
+            const float e1 = (POLY4 == 2 || (POLY4 == 1 && (i & 1))) ? ex2_poly(x1) : ex2_approx(x1);
+            ls0 += e0;
+            ls1 += e1;
+            pk[i] = H16::pack(e0, e1);
+          }
+        };
+        tmem_ld_32x16(t_s, sa);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 16, sb);
+        chunk(sa);
+        tmem_st_32x8(t_s, pk);          // P columns [0, 8) lie inside score chunk 0, already in registers
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 32, sa);
+        chunk(sb);
+        tmem_st_32x8(t_s + 8, pk);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 48, sb);
+        chunk(sa);
+        if (VAR & 4) {
+          publish(&p_half[w]);          // the stores of chunks 0 and 1 were issued a whole chunk ago
+          if (tr) stamp(j, 5 * g + 3);
+        }
+        tmem_st_32x8(t_s + 16, pk);     // columns [16, 24): score chunk 1, consumed
+        tmem_ld_wait();
+        chunk(sb);
+        tmem_st_32x8(t_s + 24, pk);
+      } else if (kv_valid >= 64) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t sc[32];
@@ -328,10 +391,9 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
             pk[i] = H16::pack(e0, e1);
           }
           tmem_st_32x16(t_s + c * 16, pk);
-          if (VAR == 4 && c == 0) {
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_half[w]);
+          if ((VAR & 4) && c == 0) {
+            publish(&p_half[w]);
+            if (tr) stamp(j, 5 * g + 3);
           }
         }
       } else {
@@ -353,17 +415,12 @@ __device__ __forceinline__ void attention_v3_body(const CUtensorMap& tmQKV, cons
             pk[i] = H16::pack(e0, e1);
           }
           tmem_st_32x16(t_s + c * 16, pk);
-          if (VAR == 4 && c == 0) {
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&p_half[w]);
-          }
+          if ((VAR & 4) && c == 0) publish(&p_half[w]);
         }
       }
       l_run += ls0 + ls1;
-      tmem_st_wait();
-      tc_fence_before();
-      mbar_arrive(&p_full[w]);
+      publish(&p_full[w]);
+      if (tr) stamp(j, 5 * g + 4);
     }
 
     // epilogue: combine the two partial row sums, O_w / l -> global (each half writes its D/2 columns)
@@ -431,26 +488,64 @@ static int launch_attention_v3p(dk_ctx* ctx, const CUtensorMap& tm, const AttPar
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
+// tuning state: [0] split, [1] poly, [2] stream; -1 = not set (kernel default).  Initialised from the environment
+// (DK_ATT_SPLIT / DK_ATT_POLY / DK_ATT_STREAM), overridable in-process through dk_attention_tuning (same-box A/Bs).
+static int g_att_tuning[3] = {-2, -2, -2};
+static int att_tuning(int i) {
+  if (g_att_tuning[i] == -2) {
+    static const char* names[3] = {"DK_ATT_SPLIT", "DK_ATT_POLY", "DK_ATT_STREAM"};
+    const char* e = getenv(names[i]);
+    g_att_tuning[i] = e ? atoi(e) : -1;
+  }
+  return g_att_tuning[i];
+}
+
 template <typename T, int D>
 static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttParams& p, cudaStream_t stream) {
-  // Tuning knobs (defaults = the best same-box A/B of round 2, profiles/r02_att_ab*.txt):
-  //   DK_ATT_SPLIT (default 1): publish P in two halves so that the PV MMAs of the first 32 keys of every thread are
-  //                 issued while the exponentials of the other 32 are still running (+4.7 % at d = 128)
-  //   DK_ATT_POLY  (default 0 for d = 128, 1 for d = 64): of every four exponentials, how many run as a cubic on the
-  //                 FMA pipe instead of MUFU.EX2 (d = 64 is MUFU-bound 2:1: 568 -> 671 TFLOP/s with split + poly 1;
-  //                 d = 128: 1133 -> 1194 with the split alone, poly costs 1-3 % there)
-  static const int poly_env = [] {
-    const char* e = getenv("DK_ATT_POLY");
-    return e ? atoi(e) : -1;
-  }();
-  static const int split_env = [] {
-    const char* e = getenv("DK_ATT_SPLIT");
-    return e ? atoi(e) : -1;
-  }();
+  // Tuning knobs (defaults = the best same-box A/Bs of round 2, profiles/r02_att_*.txt):
+  //   DK_ATT_SPLIT  (default 1): publish P in two parts so that the PV MMAs of the keys published first are issued
+  //                  while the last exponentials are still running (+4.7 % at d = 128)
+  //   DK_ATT_STREAM (default 1, needs the split): streamed exponential pass (VAR bit 32): softmax leg 2130 -> 1910
+  //                  clocks per step in the timestamp trace, +2-4 % at d = 128 and +4-8 % at d = 64 with poly 1
+  //   DK_ATT_POLY   (default 1): of every four exponentials, how many run as a cubic on the FMA pipe instead of
+  //                  MUFU.EX2 (d = 64 is MUFU-bound 2:1; at d = 128 one in four is neutral to +2 %, two cost 5-8 %)
   static const char* impl = getenv("DK_ATTENTION_IMPL");
+  const int poly_env = att_tuning(1), split_env = att_tuning(0), stream_env = att_tuning(2);
   const bool plain = impl != nullptr && impl[0] == '3' && impl[1] == 'p';   // round-1 behaviour: no split, no poly
   const bool split = !plain && (split_env >= 0 ? split_env != 0 : true);
-  const int poly = plain ? 0 : (poly_env >= 0 ? poly_env : (D == 64 ? 1 : 0));
+  const int poly = plain ? 0 : (poly_env >= 0 ? (poly_env > 2 ? 2 : poly_env) : 1);
+  const bool streamed = split && (stream_env >= 0 ? stream_env != 0 : true);
+  if constexpr (D == 128 && std::is_same<T, __nv_bfloat16>::value) {
+    // DK_ATT_TRACE=<file>: run the diagnostic instantiation (timestamps, poly 0) and dump the table
+    static const char* trace_path = getenv("DK_ATT_TRACE");
+    if (trace_path != nullptr) {
+      constexpr int N = 34 * 32;
+      long long* dbuf = nullptr;
+      DK_CHECK_CUDA(cudaMalloc(&dbuf, N * sizeof(long long)));
+      DK_CHECK_CUDA(cudaMemsetAsync(dbuf, 0, N * sizeof(long long), stream));
+      AttParams pt = p;
+      pt.trace = dbuf;
+      const int rc = streamed ? launch_attention_v3p<__nv_bfloat16, 128, 0, 4 | 16 | 32>(ctx, tm, pt, stream)
+                              : launch_attention_v3p<__nv_bfloat16, 128, 0, 4 | 16>(ctx, tm, pt, stream);
+      DK_CHECK_CUDA(cudaStreamSynchronize(stream));
+      static long long host[N];
+      DK_CHECK_CUDA(cudaMemcpy(host, dbuf, N * sizeof(long long), cudaMemcpyDeviceToHost));
+      cudaFree(dbuf);
+      if (FILE* f = fopen(trace_path, "w")) {
+        for (int i = 0; i < 34; ++i) {
+          for (int k = 0; k < 32; ++k) fprintf(f, "%lld ", host[i * 32 + k]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+      return rc;
+    }
+  }
+  if (streamed) {
+    if (poly <= 0) return launch_attention_v3p<T, D, 0, 4 | 32>(ctx, tm, p, stream);
+    if (poly == 1) return launch_attention_v3p<T, D, 1, 4 | 32>(ctx, tm, p, stream);
+    return launch_attention_v3p<T, D, 2, 4 | 32>(ctx, tm, p, stream);
+  }
   if (split) {
     if (poly <= 0) return launch_attention_v3p<T, D, 0, 4>(ctx, tm, p, stream);
     if (poly == 1) return launch_attention_v3p<T, D, 1, 4>(ctx, tm, p, stream);
@@ -464,6 +559,13 @@ static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttPara
 }  // namespace dk
 
 using namespace dk;
+
+extern "C" int dk_attention_tuning(int split, int poly, int stream) {
+  g_att_tuning[0] = split < 0 ? -1 : split;
+  g_att_tuning[1] = poly < 0 ? -1 : poly;
+  g_att_tuning[2] = stream < 0 ? -1 : stream;
+  return 0;
+}
 
 extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, int S, int heads, int d, float scale,
                                 int split, void* out0, long long ld0, void* out1, long long ld1, void* stream_) {
@@ -500,7 +602,7 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
   p.ld0 = ld0;
   p.out1 = out1;
   p.ld1 = ld1;
-  // default: v3 with the split P publication (launch_attention_v3); DK_ATTENTION_IMPL=5 selects the persistent
+  // default: v3 with the split P publication and the streamed exponential pass (launch_attention_v3); DK_ATTENTION_IMPL=5 selects the persistent
   // single-pass kernel of attention_v5.cu, 3p the round-1 form of v3
   static const bool use_v5 = [] {
     const char* e = getenv("DK_ATTENTION_IMPL");

@@ -1,7 +1,10 @@
 // Shared definitions of the attention kernels (attention.cu: v3, the default; attention_v5.cu: the persistent variant).
 #pragma once
 
+#include <stdio.h>
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "host.h"
@@ -19,6 +22,7 @@ struct AttParams {
   long long ld0;
   void* out1;
   long long ld1;
+  long long* trace = nullptr;   // diagnostic instantiation only (DK_ATT_TRACE)
 };
 
 // two 128-row Q tiles per CTA, K / V rings shared by both (v2, v2a, v3)
@@ -35,6 +39,12 @@ struct Att2Cfg {
   static constexpr int TMEM_S = 0;     // + 128 * w
   static constexpr int TMEM_O = 256;   // + 128 * w
 };
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 
 }  // namespace dk
 

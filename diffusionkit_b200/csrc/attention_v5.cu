@@ -46,11 +46,6 @@ struct Att5Cfg {
   static constexpr int TMEM_O = 256;   // + 128 * w
 };
 
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-  float d;
-  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-  return d;
-}
 __device__ __forceinline__ void xch_put(uint32_t slot, float v, uint32_t tag) {
   asm volatile("st.volatile.shared.v2.b32 [%0], {%1, %2};" ::"r"(slot), "r"(__float_as_uint(v)), "r"(tag) : "memory");
 }

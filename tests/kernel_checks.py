@@ -376,11 +376,39 @@ def check_attention_v3_explicit():
     return out
 
 
+def check_attention_v3_variants():
+    """every (split, streamed pass, poly share) setting of v3 through the in-process tuning hook: each against the fp32
+    reference, and the split / streamed forms bit-identical to the plain form with the same poly share"""
+    _setup()
+    from diffusionkit_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    try:
+        for d, dt, S in ((128, torch.bfloat16, 1300), (64, torch.float16, 1178)):
+            qkv = _rand((2 * S, 3 * 2 * d), dt)
+            for poly in (0, 1, 2):
+                base = None
+                for split, stream in ((0, 0), (1, 0), (1, 1)):
+                    lib.dk_attention_tuning(split, poly, stream)
+                    name = f"att3_d{d}_split{split}_stream{stream}_poly{poly}"
+                    out[name] = _attention_case(2, S, 2, d, dt, split=1024, name=name)
+                    o = torch.zeros((2 * S, 2 * d), dtype=dt, device=DEV)
+                    ops.attention(qkv, 2, S, 2, d, o)
+                    if base is None:
+                        base = o
+                    else:
+                        assert torch.equal(o, base), f"{name}: not bit-identical to the plain form"
+    finally:
+        lib.dk_attention_tuning(-1, -1, -1)
+    return out
+
+
 def check_attention_v3s_kernel():
-    """v3 with the split P publication (DK_ATTENTION_IMPL=3s): the PV MMAs of the first 32 keys of every thread are issued
-    while the exponentials of the other 32 are still running"""
+    """v3 with the split P publication but the two-round exponential pass (DK_ATT_STREAM=0): the PV MMAs of the first 32
+    keys of every thread are issued while the exponentials of the other 32 are still running"""
     os.environ["DK_ATTENTION_IMPL"] = "3"
     os.environ["DK_ATT_SPLIT"] = "1"
+    os.environ["DK_ATT_STREAM"] = "0"
     os.environ["DK_ATT_POLY"] = "1"
     _setup()
     out = {"d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att3s_d128_S128"),
@@ -979,7 +1007,7 @@ ALL_CHECKS = [
     check_gemm_pair_kernel, check_gemm_pair_legacy_store, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
     check_text_kernels, check_attention_small,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
-    check_attention_v3_explicit, check_attention_v3s_kernel, check_attention_v5_kernel,
+    check_attention_v3_explicit, check_attention_v3s_kernel, check_attention_v3_variants, check_attention_v5_kernel,
     check_conv_fused,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,
