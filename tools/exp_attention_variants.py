@@ -1,6 +1,6 @@
 """Same-process A/B of the K3 (attention v3) tuning variants through dk_attention_tuning: every (poly, stream) pair is
 checked against the default kernel's output on the same inputs (bit-exact for equal poly; rel-L2 across poly) and timed.
-  python tools/exp_attention_flags.py [rounds]"""
+  python tools/exp_attention_variants.py [rounds]"""
 import os
 import sys
 
