@@ -506,14 +506,16 @@ static int launch_attention_v3(dk_ctx* ctx, const CUtensorMap& tm, const AttPara
   //   DK_ATT_SPLIT  (default 1): publish P in two parts so that the PV MMAs of the keys published first are issued
   //                  while the last exponentials are still running (+4.7 % at d = 128)
   //   DK_ATT_STREAM (default 1, needs the split): streamed exponential pass (VAR bit 32): softmax leg 2130 -> 1910
-  //                  clocks per step in the timestamp trace, +2-4 % at d = 128 and +4-8 % at d = 64 with poly 1
-  //   DK_ATT_POLY   (default 1): of every four exponentials, how many run as a cubic on the FMA pipe instead of
-  //                  MUFU.EX2 (d = 64 is MUFU-bound 2:1; at d = 128 one in four is neutral to +2 %, two cost 5-8 %)
+  //                  clocks per step in the timestamp trace; over six same-box sweeps +1-3 % at S = 4352 / d = 128,
+  //                  +5-7 % at S = 1280 (C2) and +4-5 % at d = 64
+  //   DK_ATT_POLY   (default 0 for d = 128, 1 for d = 64): of every four exponentials, how many run as a cubic on the
+  //                  FMA pipe instead of MUFU.EX2 (d = 64 is MUFU-bound 2:1: +8-10 %; at d = 128 one in four is a tie
+  //                  at S = 4352 and costs 7 % at S = 1280, two cost 5-10 %)
   static const char* impl = getenv("DK_ATTENTION_IMPL");
   const int poly_env = att_tuning(1), split_env = att_tuning(0), stream_env = att_tuning(2);
   const bool plain = impl != nullptr && impl[0] == '3' && impl[1] == 'p';   // round-1 behaviour: no split, no poly
   const bool split = !plain && (split_env >= 0 ? split_env != 0 : true);
-  const int poly = plain ? 0 : (poly_env >= 0 ? (poly_env > 2 ? 2 : poly_env) : 1);
+  const int poly = plain ? 0 : (poly_env >= 0 ? (poly_env > 2 ? 2 : poly_env) : (D == 64 ? 1 : 0));
   const bool streamed = split && (stream_env >= 0 ? stream_env != 0 : true);
   if constexpr (D == 128 && std::is_same<T, __nv_bfloat16>::value) {
     // DK_ATT_TRACE=<file>: run the diagnostic instantiation (timestamps, poly 0) and dump the table

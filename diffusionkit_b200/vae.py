@@ -149,6 +149,14 @@ class VAEDecoder(_VAEBlocks):
         self.up_w = {k[:-len(".weight")]: ops.conv_up_weights(v) for k, v in self.p.items()
                      if k.endswith(".upsample.weight")}
         self.use_fused = os.environ.get("DK_VAE_FUSED", "1") != "0"
+        # where GroupNorm-apply + SiLU runs on the fused path: "1" (default) = inside the convolution, on the staged halo
+        # tile (no normalised tensor in HBM; every halo element is transformed once per CTA that stages it: 2x for the
+        # two halo rows of a 2-row tile, times Cout/128 n-tiles); "0" = one HBM pass of the apply kernel in front of the
+        # fused convolution (which still folds bias / skip / upsample / the next statistics).  Whole 1024^2 decode, same
+        # box (profiles/r02_vae_norm_mode.txt): 42.1 / 43.6 ms inside vs 41.9 / 40.3 ms separate at batch 4, 10.75 vs
+        # 10.24 ms at batch 1 — a 2-5 % difference for 33 % more launches and ~2 GB more HBM traffic per image, so
+        # the in-kernel form stays the default.
+        self.norm_in_conv = os.environ.get("DK_VAE_NORM_IN_CONV", "1") != "0"
         self.use_cuda_graphs = os.environ.get("DK_CUDA_GRAPHS", "1") != "0"
         self._shapes: "OrderedDict[tuple, tuple]" = OrderedDict()     # input shape -> (graph, static in, static out, launches)
         self.max_cached_shapes = int(os.environ.get("DK_MAX_CACHED_SHAPES", "4"))
@@ -164,8 +172,13 @@ class VAEDecoder(_VAEBlocks):
         B, H, W, C = x.shape
         if self._fused_ok(x, w.shape[0]):
             part = torch.empty((B, H * W // 128, self.groups, 2), dtype=torch.float32, device=self.device)
-            y = ops.conv3x3_fused(x, w, bias=b, res=res, gn=(st.get(), self.p[norm + ".weight"], self.p[norm + ".bias"],
-                                                             self.groups), silu=True, out_partial=part, out_G=self.groups)
+            if self.norm_in_conv:
+                y = ops.conv3x3_fused(x, w, bias=b, res=res, gn=(st.get(), self.p[norm + ".weight"],
+                                                                 self.p[norm + ".bias"], self.groups), silu=True,
+                                      out_partial=part, out_G=self.groups)
+            else:
+                xn = ops.groupnorm_apply(x, st.get(), self.p[norm + ".weight"], self.p[norm + ".bias"], self.groups, True)
+                y = ops.conv3x3_fused(xn, w, bias=b, res=res, out_partial=part, out_G=self.groups)
             return y, _Stats(self, y, part)
         xn = ops.groupnorm_apply(x, st.get(), self.p[norm + ".weight"], self.p[norm + ".bias"], self.groups, True)
         y = ops.conv3x3(xn, w, b, res=res)

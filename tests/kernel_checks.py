@@ -378,7 +378,8 @@ def check_attention_v3_explicit():
 
 def check_attention_v3_variants():
     """every (split, streamed pass, poly share) setting of v3 through the in-process tuning hook: each against the fp32
-    reference, and the split / streamed forms bit-identical to the plain form with the same poly share"""
+    reference; the streamed pass is bit-identical to the two-round pass with the same poly share (the split publication
+    alone changes the order in which the PV MMAs accumulate, so it is only compared with the reference)"""
     _setup()
     from diffusionkit_b200 import _lib
     lib = _lib.load()
@@ -394,10 +395,10 @@ def check_attention_v3_variants():
                     out[name] = _attention_case(2, S, 2, d, dt, split=1024, name=name)
                     o = torch.zeros((2 * S, 2 * d), dtype=dt, device=DEV)
                     ops.attention(qkv, 2, S, 2, d, o)
-                    if base is None:
+                    if split and base is None:
                         base = o
-                    else:
-                        assert torch.equal(o, base), f"{name}: not bit-identical to the plain form"
+                    elif split:
+                        assert torch.equal(o, base), f"{name}: not bit-identical to the two-round pass"
     finally:
         lib.dk_attention_tuning(-1, -1, -1)
     return out
