@@ -452,6 +452,11 @@ conv_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           float v[32];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
+            if (n0 + j * 8 >= p.Cout) {   // narrow output tile (conv_out): channels beyond Cout do not exist
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[j * 8 + i] = 0.f;
+              continue;
+            }
             float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (bias != nullptr) {
               const uint4 b4 = *reinterpret_cast<const uint4*>(bias + n0 + j * 8);
@@ -570,7 +575,10 @@ using namespace dk;
 static bool cf_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 extern "C" int dk_conv_fused_supported(int H, int W, int Cin, int Cout) {
-  return (W % CF_TW == 0 && H % (2 * CF_R) == 0 && Cin % 64 == 0 && Cin <= 512 && Cout % CF_BN == 0) ? 1 : 0;
+  // Cout: whole 128-channel tiles, or ONE narrow tile of 8..120 channels (conv_out: the weight rows beyond Cout are
+  // zero-filled by the TMA unit, the epilogue stores only the real channels)
+  const bool cout_ok = Cout % CF_BN == 0 || (Cout > 0 && Cout < CF_BN && Cout % 8 == 0);
+  return (W % CF_TW == 0 && H % (2 * CF_R) == 0 && Cin % 64 == 0 && Cin <= 512 && cout_ok) ? 1 : 0;
 }
 
 extern "C" int dk_conv_up_weights(dk_ctx* ctx, int dtype, const void* w, void* wp, int Cout, int Cin, void* stream_) {
@@ -602,8 +610,11 @@ extern "C" int dk_conv3x3_fused(dk_ctx* ctx, int dtype, const void* x, const voi
   DkDeviceGuard dk_guard_(ctx);
   DK_REQUIRE(dtype == DK_BF16 || dtype == DK_FP16, "dk_conv3x3_fused: bad dtype %d", dtype);
   DK_REQUIRE(B > 0 && dk_conv_fused_supported(H, W, Cin, Cout),
-             "dk_conv3x3_fused: needs W %% 128 == 0, H %% 4 == 0, Cin %% 64 == 0 (<= 512), Cout %% 128 == 0 (got %dx%d, %d -> %d)",
+             "dk_conv3x3_fused: needs W %% 128 == 0, H %% 4 == 0, Cin %% 64 == 0 (<= 512), Cout %% 128 == 0 or a multiple "
+             "of 8 below 128 (got %dx%d, %d -> %d)",
              H, W, Cin, Cout);
+  DK_REQUIRE(Cout % CF_BN == 0 || (up == 0 && out_partial == nullptr),
+             "dk_conv3x3_fused: a narrow output tile (Cout = %d) has no upsampling and no output statistics", Cout);
   DK_REQUIRE(cf_aligned16(x) && cf_aligned16(w) && cf_aligned16(out) && (bias == nullptr || cf_aligned16(bias)) &&
                  (res == nullptr || cf_aligned16(res)),
              "dk_conv3x3_fused: buffers must be 16-byte aligned");
@@ -622,7 +633,7 @@ extern "C" int dk_conv3x3_fused(dk_ctx* ctx, int dtype, const void* x, const voi
   p.up = up ? 1 : 0;
   p.tiles_x = W / CF_TW;
   p.tiles_y = H / (2 * CF_R);
-  p.n_tiles = Cout / CF_BN;
+  p.n_tiles = (Cout + CF_BN - 1) / CF_BN;
   p.bias = bias;
   p.res = res;
   p.out = out;

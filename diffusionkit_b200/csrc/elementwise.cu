@@ -510,17 +510,30 @@ groupnorm_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, i
     dst[1] = tq;
   }
 }
-// one warp per (b, g): lanes stride over the chunk partials (fixed lane -> chunk assignment, fixed shuffle tree:
-// deterministic), accumulation in double
-__global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int B, int G,
-                                          int chunks, double count, float eps) {
-  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (idx >= B * G) return;
+// one 256-thread block per (b, g): threads stride over the chunk partials four at a time (independent loads in
+// flight: with one warp per (b, g) the 8192 partials of a 1024^2 image were a 256-deep chain of dependent-latency
+// loads per lane, 45 us per launch x 30 launches = 11 % of a batch-1 decode), accumulation in double; fixed
+// thread -> chunk assignment, fixed shuffle tree and fixed cross-warp order: deterministic
+constexpr int GNF_THREADS = 256;
+__global__ void __launch_bounds__(GNF_THREADS)
+groupnorm_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int B, int G, int chunks,
+                          double count, float eps) {
+  const int idx = blockIdx.x;   // b * G + g
   const int b = idx / G, g = idx % G;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float2* base = reinterpret_cast<const float2*>(partial) + static_cast<long long>(b) * chunks * G + g;
   double s = 0.0, q = 0.0;
-  for (int c = lane; c < chunks; c += 32) {
-    const float2 p = *reinterpret_cast<const float2*>(partial + ((static_cast<long long>(b) * chunks + c) * G + g) * 2);
+  int c = t;
+  for (; c + 3 * GNF_THREADS < chunks; c += 4 * GNF_THREADS) {
+    const float2 p0 = base[static_cast<long long>(c) * G];
+    const float2 p1 = base[static_cast<long long>(c + GNF_THREADS) * G];
+    const float2 p2 = base[static_cast<long long>(c + 2 * GNF_THREADS) * G];
+    const float2 p3 = base[static_cast<long long>(c + 3 * GNF_THREADS) * G];
+    s += (static_cast<double>(p0.x) + p1.x) + (static_cast<double>(p2.x) + p3.x);
+    q += (static_cast<double>(p0.y) + p1.y) + (static_cast<double>(p2.y) + p3.y);
+  }
+  for (; c < chunks; c += GNF_THREADS) {
+    const float2 p = base[static_cast<long long>(c) * G];
     s += p.x;
     q += p.y;
   }
@@ -529,9 +542,21 @@ __global__ void groupnorm_finalize_kernel(const float* __restrict__ partial, flo
     s += __shfl_xor_sync(0xffffffffu, s, o);
     q += __shfl_xor_sync(0xffffffffu, q, o);
   }
+  __shared__ double red[2][GNF_THREADS / 32];
   if (lane == 0) {
-    const double mean = s / count;
-    double var = q / count - mean * mean;
+    red[0][warp] = s;
+    red[1][warp] = q;
+  }
+  __syncthreads();
+  if (t == 0) {
+    double ss = 0.0, qq = 0.0;
+#pragma unroll
+    for (int w = 0; w < GNF_THREADS / 32; ++w) {
+      ss += red[0][w];
+      qq += red[1][w];
+    }
+    const double mean = ss / count;
+    double var = qq / count - mean * mean;
     if (var < 0.0) var = 0.0;
     stats[idx * 2] = static_cast<float>(mean);
     stats[idx * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
@@ -965,8 +990,8 @@ extern "C" int dk_groupnorm_stats(dk_ctx* ctx, int dtype, const void* x, float* 
   DK_DISPATCH(dtype, (groupnorm_partial_kernel<T><<<grid, GN_THREADS, (2 * C + 2 * GN_THREADS * 8) * sizeof(float), stream>>>(
                          static_cast<const T*>(x), ws, HW, C, G, chunks)));
   DK_LAUNCH_CHECK(ctx);
-  groupnorm_finalize_kernel<<<(B * G * 32 + 127) / 128, 128, 0, stream>>>(
-      ws, stats, B, G, chunks, static_cast<double>(HW) * (C / G), eps);
+  groupnorm_finalize_kernel<<<B * G, GNF_THREADS, 0, stream>>>(ws, stats, B, G, chunks,
+                                                                static_cast<double>(HW) * (C / G), eps);
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -978,7 +1003,7 @@ extern "C" int dk_groupnorm_finalize(dk_ctx* ctx, const float* partial, float* s
   DK_REQUIRE(partial != nullptr && stats != nullptr && B > 0 && G > 0 && slots > 0 && count > 0,
              "dk_groupnorm_finalize: bad arguments");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  groupnorm_finalize_kernel<<<(B * G * 32 + 127) / 128, 128, 0, stream>>>(partial, stats, B, G, slots, count, eps);
+  groupnorm_finalize_kernel<<<B * G, GNF_THREADS, 0, stream>>>(partial, stats, B, G, slots, count, eps);
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }

@@ -243,8 +243,17 @@ class VAEDecoder(_VAEBlocks):
                 h, st = self._resnet_f(h, st, f"up_blocks.{j}.resnets.{l}")
             if f"up_blocks.{j}.upsample.weight" in self.p:
                 h, st = self._upsample_conv(h, f"up_blocks.{j}.upsample")             # vae.py:146-147
+        w_out = self.p["conv_out.weight"]                             # 3 real output channels padded to 8
+        if self._fused_ok(h, w_out.shape[0]) and self.norm_in_conv:
+            # conv_norm_out + SiLU + conv_out in the halo-tiled kernel (one narrow 8-channel output tile): the input
+            # crosses L2 -> SM once instead of nine times (the nine-box implicit GEMM ran this layer at 0.9 TB/s)
+            return ops.conv3x3_fused(h, w_out, bias=self.p["conv_out.bias"],
+                                     gn=(st.get(), self.p["conv_norm_out.weight"], self.p["conv_norm_out.bias"],
+                                         self.groups), silu=True)
         hn = ops.groupnorm_apply(h, st.get(), self.p["conv_norm_out.weight"], self.p["conv_norm_out.bias"], self.groups,
                                  True)
+        if self._fused_ok(hn, w_out.shape[0]):
+            return ops.conv3x3_fused(hn, w_out, bias=self.p["conv_out.bias"])
         return self._conv(hn, "conv_out")                             # (B, 8H, 8W, 8) — 3 real channels
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:

@@ -807,6 +807,9 @@ def check_conv_fused():
     out["up_256"] = _conv_fused_case(1, 8, 128, 256, 256, bf, False, True, False, True, "cf_up", tol=6e-3)
     out["up_b2_512"] = _conv_fused_case(2, 4, 256, 512, 512, bf, False, True, False, False, "cf_up512", tol=6e-3)
     out["fp16_norm"] = _conv_fused_case(1, 8, 128, 64, 128, torch.float16, True, False, True, True, "cf_fp16")
+    # narrow output tile (conv_out: 3 real channels padded to 8; weight rows beyond Cout zero-filled by TMA)
+    out["narrow_norm_128to8"] = _conv_fused_case(2, 8, 256, 128, 8, bf, True, False, False, False, "cf_narrow8", tol=6e-3)
+    out["narrow_plain_64to64"] = _conv_fused_case(1, 4, 128, 64, 64, bf, False, False, True, False, "cf_narrow64")
     return out
 
 
