@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdkb200.so")
-SOURCES = ["api.cu", "gemm.cu", "gemm2.cu", "conv_fused.cu", "attention.cu", "attention_v5.cu", "elementwise.cu", "text.cu"]
+SOURCES = ["api.cu", "gemm.cu", "gemm2.cu", "conv_fused.cu", "attention.cu", "attention_v5.cu", "attention_v6.cu", "elementwise.cu", "text.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

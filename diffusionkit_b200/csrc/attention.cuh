@@ -51,3 +51,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
 // v5 (attention_v5.cu, DK_ATTENTION_IMPL=5): persistent CTAs, register-resident scores, speculative exponentials
 int dk_launch_attention_v5(dk_ctx* ctx, int dtype, int d, const CUtensorMap& tm, const dk::AttParams& p,
                            cudaStream_t stream);
+
+// v6 (attention_v6.cu, DK_ATTENTION_IMPL=6): 64-key steps with double-buffered score accumulators
+int dk_launch_attention_v6(dk_ctx* ctx, int dtype, int d, int poly, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
+                           const dk::AttParams& p, cudaStream_t stream);

@@ -439,6 +439,24 @@ def check_attention_v5_kernel():
     return out
 
 
+def check_attention_v6_kernel():
+    """64-key steps with double-buffered score accumulators (DK_ATTENTION_IMPL=6): one and many steps, odd / even step
+    counts, ragged tails (incl. a fully masked 32-key half), both head dims, split outputs, poly share, lazy rescale
+    (which has to wait for the previous PV here)"""
+    os.environ["DK_ATTENTION_IMPL"] = "6"
+    _setup()
+    out = {"d128_S64": _attention_case(1, 64, 1, 128, torch.bfloat16, name="att6_d128_S64"),
+           "d128_S128": _attention_case(1, 128, 1, 128, torch.bfloat16, name="att6_d128_S128"),
+           "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att6_d128_S300"),
+           "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att6_d128_S1280"),
+           "d128_S4400": _attention_case(1, 4400, 2, 128, torch.bfloat16, name="att6_d128_S4400"),
+           "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att6_d64_S1178"),
+           "d64_S333": _attention_case(1, 333, 2, 64, torch.bfloat16, name="att6_d64_S333"),
+           "S1": _attention_case(2, 1, 2, 128, torch.bfloat16, name="att6_S1")}
+    out["rescale"] = check_attention_large_scores()["err"]
+    return out
+
+
 def check_attention_large_scores():
     """rows whose running max keeps growing: exercises the lazy O rescale path."""
     _setup()
@@ -1011,7 +1029,7 @@ ALL_CHECKS = [
     check_gemm_pair_kernel, check_gemm_pair_legacy_store, check_conv3x3, check_conv3x3_s2, check_img2img_kernels, check_dequant_q4,
     check_text_kernels, check_attention_small,
     check_attention_d128_one_tile, check_attention_d128, check_attention_d64, check_attention_large_scores,
-    check_attention_v3_explicit, check_attention_v3s_kernel, check_attention_v3_variants, check_attention_v5_kernel,
+    check_attention_v3_explicit, check_attention_v3s_kernel, check_attention_v3_variants, check_attention_v5_kernel, check_attention_v6_kernel,
     check_conv_fused,
     check_ln_modulate, check_qk_norm_rope, check_layout_kernels, check_sampler_kernels, check_groupnorm,
     check_softmax_image_post, check_edge_cases, check_error_paths,

@@ -14,7 +14,7 @@ sys.path.insert(0, HERE)
 # checks that select a non-default kernel through an environment variable the library latches on first use:
 # they need a process of their own
 ISOLATED = {"check_gemm_pair_kernel", "check_gemm_pair_legacy_store", "check_attention_v3_explicit",
-            "check_attention_v3s_kernel", "check_attention_v5_kernel"}
+            "check_attention_v3s_kernel", "check_attention_v5_kernel", "check_attention_v6_kernel"}
 
 
 def pytest_generate_tests(metafunc):
