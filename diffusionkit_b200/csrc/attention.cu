@@ -611,16 +611,17 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
     return e != nullptr && e[0] == '5';
   }();
   if (use_v5) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
-  static const bool env_v6 = [] {
+  static const int env_v6 = [] {   // 6: two threads per row, 7: one thread per row
     const char* e = getenv("DK_ATTENTION_IMPL");
-    return e != nullptr && e[0] == '6';
+    return (e != nullptr && (e[0] == '6' || e[0] == '7')) ? e[0] - '0' : 0;
   }();
-  if (env_v6 || att_tuning(2) == 2) {   // 64-key steps, double-buffered scores (attention_v6.cu)
+  if (env_v6 != 0 || att_tuning(2) == 2 || att_tuning(2) == 3) {   // 64-key steps, double-buffered scores (attention_v6.cu)
+    const int one = (env_v6 == 7 || att_tuning(2) == 3) ? 1 : 0;
     CUtensorMap tm64;
     const uint32_t box64[2] = {64, 64};
     if (int rc = dk_make_tmap_16b(ctx, &tm64, qkv, 2, dims, strides, box64)) return rc;
     const int pe = att_tuning(1);
-    return dk_launch_attention_v6(ctx, dtype, d, pe >= 0 ? pe : (d == 64 ? 1 : 0), tm, tm64, p, stream);
+    return dk_launch_attention_v6(ctx, dtype, d, pe >= 0 ? pe : (d == 64 ? 1 : 0), one, tm, tm64, p, stream);
   }
   if (dtype == DK_BF16) {
     if (d == 128) return launch_attention_v3<__nv_bfloat16, 128>(ctx, tm, p, stream);

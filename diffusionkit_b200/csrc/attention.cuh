@@ -53,5 +53,5 @@ int dk_launch_attention_v5(dk_ctx* ctx, int dtype, int d, const CUtensorMap& tm,
                            cudaStream_t stream);
 
 // v6 (attention_v6.cu, DK_ATTENTION_IMPL=6): 64-key steps with double-buffered score accumulators
-int dk_launch_attention_v6(dk_ctx* ctx, int dtype, int d, int poly, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
-                           const dk::AttParams& p, cudaStream_t stream);
+int dk_launch_attention_v6(dk_ctx* ctx, int dtype, int d, int poly, int one_thread_per_row, const CUtensorMap& tmQ,
+                           const CUtensorMap& tmKV, const dk::AttParams& p, cudaStream_t stream);

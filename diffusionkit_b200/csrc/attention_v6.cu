@@ -21,7 +21,11 @@
 
 namespace dk {
 
-constexpr int ATT6_THREADS = 576;   // warps 0-15 softmax (g = warp >> 2: tile = g >> 1, half = g & 1), 16 TMA, 17 MMA
+// ONE = 0: 576 threads, warps 0-15 softmax (g = warp >> 2: tile = g >> 1, half = g & 1; two threads per row), 16 TMA, 17 MMA
+// ONE = 1: 320 threads, warps 0-7 softmax (tile = warp >> 2; ONE thread per row: 64 scores per step in registers, no
+//          maximum exchange, half the mbarrier arrivals; up to 200 registers per thread), 8 TMA, 9 MMA
+constexpr int ATT6_THREADS = 576;
+constexpr int ATT6_THREADS_ONE = 320;
 constexpr int ATT6_BKV = 64;
 
 template <int D>
@@ -42,13 +46,14 @@ struct Att6Cfg {
   static constexpr int TMEM_O = 256;   // + w * 128
 };
 
-template <typename T, int D, int POLY4>
-__global__ void __launch_bounds__(ATT6_THREADS, 1)
+template <typename T, int D, int POLY4, int ONE>
+__global__ void __launch_bounds__(ONE ? ATT6_THREADS_ONE : ATT6_THREADS, 1)
 attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const AttParams p) {
   using H16 = Half16<T>;
   using Cfg = Att6Cfg<D>;
   constexpr int KS = Cfg::KS;
+  constexpr int W_TMA = ONE ? 8 : 16, W_MMA = ONE ? 9 : 17;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + Cfg::OFF_Q;
@@ -76,7 +81,7 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int n_steps = (p.S + ATT6_BKV - 1) / ATT6_BKV;
   const int row_base = b * p.S;
 
-  if (warp == 16 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
     mbar_init(q_full, 1);
@@ -88,14 +93,14 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 256);
+      mbar_init(&p_full[i], ONE ? 128 : 256);
       mbar_init(&pv_done[i], 1);
     }
     mbar_init(&o_full[0], 1);
     mbar_init(&o_full[1], 1);
     fence_barrier_init();
   }
-  if (warp == 17) {
+  if (warp == W_MMA) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -104,7 +109,7 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 16) {
+  if (warp == W_TMA) {
     // -------------------------------------------------------------------- TMA producer (converged warp, elected issue)
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(q_full, 2 * Cfg::Q_BYTES);
@@ -140,7 +145,7 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         par ^= 1;
       }
     }
-  } else if (warp == 17) {
+  } else if (warp == W_MMA) {
     // -------------------------------------------------------------------- MMA issuer (converged warp, elected issue)
     constexpr uint32_t idesc_qk = make_idesc_f16(ATT_BQ, ATT6_BKV, H16::is_bf16, false, false);
     constexpr uint32_t idesc_pv = make_idesc_f16(ATT_BQ, D, H16::is_bf16, false, true);
@@ -163,14 +168,14 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       umma_commit(&s_full[w * 2 + bb]);
     };
     // O_w += P_w V: A = P_w from TMEM (16 keys = 8 packed columns per slice: keys 0-31 in columns [0,16) of the buffer,
-    // keys 32-63 in [32,48)), B = V slice of 16 key rows (2048 B apart)
+    // keys 32-63 in [32,48); ONE: keys 0-63 in columns [0,32)), B = V slice of 16 key rows (2048 B apart)
     auto issue_pv = [&](int w, int st, int bb, bool first) {
       const uint32_t v_lo = v_lo0 + st * (Cfg::KV_BYTES >> 4);
       const uint32_t p_tmem = tmem_base + Cfg::TMEM_S + (w * 2 + bb) * 64;
       const uint32_t d_tmem = tmem_base + Cfg::TMEM_O + w * 128;
 #pragma unroll
       for (int k = 0; k < ATT6_BKV / 16; ++k)
-        umma_ts(d_tmem, p_tmem + (k >> 1) * 32 + (k & 1) * 8, smem_desc_join(v_lo + k * (2048 >> 4), desc_hi), idesc_pv,
+        umma_ts(d_tmem, p_tmem + (ONE ? k * 8 : (k >> 1) * 32 + (k & 1) * 8), smem_desc_join(v_lo + k * (2048 >> 4), desc_hi), idesc_pv,
                 (!first || k != 0) ? 1u : 0u);
       umma_commit(&pv_done[w * 2 + bb]);
     };
@@ -211,6 +216,122 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           }
         }
         __syncwarp();
+      }
+    }
+  } else if constexpr (ONE != 0) {
+    // -------------------------------------------------------------------- softmax, one thread per row
+    const int w = warp >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t t_o = t_lane + Cfg::TMEM_O + w * 128;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    const float sl2 = p.scale_log2;
+    for (int j = 0; j < n_steps; ++j) {
+      const int bb = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      const uint32_t t_s = t_lane + Cfg::TMEM_S + (w * 2 + bb) * 64;
+      mbar_wait(&s_full[w * 2 + bb], ph);
+      tc_fence_after();
+      const int kv_valid = p.S - j * ATT6_BKV;
+      uint32_t sa[32], sb[32];
+      tmem_ld_32x32(t_s, sa);
+      tmem_ld_32x32(t_s + 32, sb);
+      tmem_ld_wait();
+      if (kv_valid < 64) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= kv_valid) sa[i] = 0xff800000u;
+          if (32 + i >= kv_valid) sb[i] = 0xff800000u;
+        }
+      }
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        m4[0] = fmaxf(m4[0], __uint_as_float(sa[i]));
+        m4[1] = fmaxf(m4[1], __uint_as_float(sa[i + 1]));
+        m4[2] = fmaxf(m4[2], __uint_as_float(sb[i]));
+        m4[3] = fmaxf(m4[3], __uint_as_float(sb[i + 1]));
+      }
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * sl2;
+      const float m_new = fmaxf(m_run, mx);
+      const bool need = (m_new - m_run) > 8.0f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float alpha = ex2_approx(m_run - m_new);
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+          mbar_wait(&pv_done[w * 2 + (bb ^ 1)], ((j - 1) >> 1) & 1);   // O is quiescent once PV(j-1) has retired
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < D / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x16(t_o + c * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(t_o + c * 16, o);
+          }
+        }
+      }
+      float ls0 = 0.f, ls1 = 0.f;
+      {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sa[2 * i]), sl2, -m_run));
+          const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sl2, -m_run);
+          const float e1 = (POLY4 == 2 || (POLY4 == 1 && (i & 1))) ? ex2_poly(x1) : ex2_approx(x1);
+          ls0 += e0;
+          ls1 += e1;
+          pk[i] = H16::pack(e0, e1);
+        }
+        tmem_st_32x16(t_s, pk);          // P columns [0,16): keys 0-31 (scores already in registers)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sb[2 * i]), sl2, -m_run));
+          const float x1 = fmaf(__uint_as_float(sb[2 * i + 1]), sl2, -m_run);
+          const float e1 = (POLY4 == 2 || (POLY4 == 1 && (i & 1))) ? ex2_poly(x1) : ex2_approx(x1);
+          ls0 += e0;
+          ls1 += e1;
+          pk[i] = H16::pack(e0, e1);
+        }
+        tmem_st_32x16(t_s + 16, pk);     // P columns [16,32): keys 32-63
+      }
+      l_run += ls0 + ls1;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[w * 2 + bb]);
+    }
+    mbar_wait(&o_full[w], 0);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int s_idx = q0 + w * ATT_BQ + r;
+    const bool row_ok = s_idx < p.S;
+    T* dst = nullptr;
+    if (row_ok) {
+      if (s_idx < p.split)
+        dst = reinterpret_cast<T*>(p.out0) + (static_cast<long long>(b) * p.split + s_idx) * p.ld0 + head * D;
+      else
+        dst = reinterpret_cast<T*>(p.out1) +
+              (static_cast<long long>(b) * (p.S - p.split) + (s_idx - p.split)) * p.ld1 + head * D;
+    }
+#pragma unroll
+    for (int c = 0; c < D / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_o + c * 32, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          uint4 pk4;
+          pk4.x = H16::pack(__uint_as_float(o[gq * 8 + 0]) * inv_l, __uint_as_float(o[gq * 8 + 1]) * inv_l);
+          pk4.y = H16::pack(__uint_as_float(o[gq * 8 + 2]) * inv_l, __uint_as_float(o[gq * 8 + 3]) * inv_l);
+          pk4.z = H16::pack(__uint_as_float(o[gq * 8 + 4]) * inv_l, __uint_as_float(o[gq * 8 + 5]) * inv_l);
+          pk4.w = H16::pack(__uint_as_float(o[gq * 8 + 6]) * inv_l, __uint_as_float(o[gq * 8 + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + gq * 8) = pk4;
+        }
       }
     }
   } else {
@@ -334,24 +455,24 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 17) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
-template <typename T, int D, int POLY4>
+template <typename T, int D, int POLY4, int ONE>
 static int launch_attention_v6p(dk_ctx* ctx, const CUtensorMap& tmQ, const CUtensorMap& tmKV, const AttParams& p,
                                 cudaStream_t stream) {
   using Cfg = Att6Cfg<D>;
-  auto kern = attention_fwd_v6_kernel<T, D, POLY4>;
+  auto kern = attention_fwd_v6_kernel<T, D, POLY4, ONE>;
   static bool configured = false;
   if (!configured) {
     DK_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   dim3 grid(dk_ceil_div(p.S, 2 * ATT_BQ), p.heads, p.B);
-  kern<<<grid, ATT6_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+  kern<<<grid, ONE ? ATT6_THREADS_ONE : ATT6_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmKV, p);
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -359,15 +480,20 @@ static int launch_attention_v6p(dk_ctx* ctx, const CUtensorMap& tmQ, const CUten
 }  // namespace dk
 
 // tmQ: the [B*S, 3*heads*d] tensor map with 128-row boxes (dk_attention_fwd builds it); tmKV: the same tensor with
-// 64-row boxes.  poly: exponentials per four on the FMA pipe (0..2).
-int dk_launch_attention_v6(dk_ctx* ctx, int dtype, int d, int poly, const CUtensorMap& tmQ, const CUtensorMap& tmKV,
-                           const dk::AttParams& p, cudaStream_t stream) {
+// 64-row boxes.  poly: exponentials per four on the FMA pipe (0..2).  one_thread_per_row: the 320-thread form.
+int dk_launch_attention_v6(dk_ctx* ctx, int dtype, int d, int poly, int one_thread_per_row, const CUtensorMap& tmQ,
+                           const CUtensorMap& tmKV, const dk::AttParams& p, cudaStream_t stream) {
   using namespace dk;
-#define DK_V6(TT, DD)                                                                   \
-  do {                                                                                  \
-    if (poly <= 0) return launch_attention_v6p<TT, DD, 0>(ctx, tmQ, tmKV, p, stream);   \
-    if (poly == 1) return launch_attention_v6p<TT, DD, 1>(ctx, tmQ, tmKV, p, stream);   \
-    return launch_attention_v6p<TT, DD, 2>(ctx, tmQ, tmKV, p, stream);                  \
+#define DK_V6(TT, DD)                                                                          \
+  do {                                                                                         \
+    if (one_thread_per_row) {                                                                  \
+      if (poly <= 0) return launch_attention_v6p<TT, DD, 0, 1>(ctx, tmQ, tmKV, p, stream);     \
+      if (poly == 1) return launch_attention_v6p<TT, DD, 1, 1>(ctx, tmQ, tmKV, p, stream);     \
+      return launch_attention_v6p<TT, DD, 2, 1>(ctx, tmQ, tmKV, p, stream);                    \
+    }                                                                                          \
+    if (poly <= 0) return launch_attention_v6p<TT, DD, 0, 0>(ctx, tmQ, tmKV, p, stream);       \
+    if (poly == 1) return launch_attention_v6p<TT, DD, 1, 0>(ctx, tmQ, tmKV, p, stream);       \
+    return launch_attention_v6p<TT, DD, 2, 0>(ctx, tmQ, tmKV, p, stream);                      \
   } while (0)
   if (dtype == DK_BF16) {
     if (d == 128) DK_V6(__nv_bfloat16, 128);

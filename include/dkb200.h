@@ -131,8 +131,8 @@ int dk_qk_norm_rope(dk_ctx* ctx, int dtype, void* qkv, int rows, int S, int head
 int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, int S, int heads, int d, float scale, int split,
                      void* out0, long long ld0, void* out1, long long ld1, void* stream);
 /* Tuning hook for same-process A/B measurements of the K3 variants (no reference counterpart): split P publication
- * (0/1), exponentials per four evaluated on the FMA pipe (0..2), streamed exponential pass (0/1; 2 selects the 64-key
- * double-buffered kernel of attention_v6.cu); a negative value
+ * (0/1), exponentials per four evaluated on the FMA pipe (0..2), streamed exponential pass (0/1; 2 / 3 select the 64-key
+ * double-buffered kernel of attention_v6.cu with two threads / one thread per row); a negative value
  * restores the built-in default / environment setting.  Results are bit-identical for every setting of split and
  * stream; poly changes P below its 16-bit rounding. */
 int dk_attention_tuning(int split, int poly, int stream);

@@ -1037,5 +1037,22 @@ ALL_CHECKS = [
 
 # kernels behind an environment knob that have not been measured / validated on hardware yet: not part of the pytest
 # suite; `python tools/run_gpu_checks.py +experimental <name>` runs them
-EXPERIMENTAL_CHECKS = []
+def check_attention_v6_one_thread_per_row():
+    """the 320-thread form of v6 (one thread per row; in-process selection: dk_attention_tuning stream = 3).  Run on
+    hardware in round 2 (profiles/r02_att_v6_one_call34.txt); outside the pytest suite because it is not a default."""
+    _setup()
+    from diffusionkit_b200 import _lib
+    lib = _lib.load()
+    lib.dk_attention_tuning(-1, -1, 3)
+    try:
+        return {"d128_S64": _attention_case(1, 64, 1, 128, torch.bfloat16, name="att7_d128_S64"),
+                "d128_S300": _attention_case(2, 300, 2, 128, torch.bfloat16, name="att7_d128_S300"),
+                "d128_S1280_split": _attention_case(1, 1280, 3, 128, torch.bfloat16, split=256, name="att7_d128_S1280"),
+                "d64_S1178_split": _attention_case(2, 1178, 2, 64, torch.float16, split=1024, name="att7_d64_S1178"),
+                "rescale": check_attention_large_scores()["err"]}
+    finally:
+        lib.dk_attention_tuning(-1, -1, -1)
+
+
+EXPERIMENTAL_CHECKS = [check_attention_v6_one_thread_per_row]
 

@@ -13,6 +13,7 @@ from diffusionkit_b200 import _lib, ops  # noqa: E402
 
 lib = _lib.load()
 DEV = "cuda:0"
+MODE = int(os.environ.get("V6_MODE", "2"))   # dk_attention_tuning stream value: 2 = two threads per row, 3 = one
 
 
 def timeit(fn, iters=100, warm=5):
@@ -36,10 +37,10 @@ if sys.argv[1] == "check":
     kc._setup()
     dt = torch.bfloat16 if d == 128 else torch.float16
     for poly in (0, 1):
-        lib.dk_attention_tuning(1, poly, 2)
+        lib.dk_attention_tuning(1, poly, MODE)
         err = kc._attention_case(B, S, heads, d, dt, split=split, name=f"att6_B{B}_S{S}_h{heads}_d{d}_poly{poly}")
         torch.cuda.synchronize()
-        print(f"v6 B{B} S{S} heads{heads} d{d} split{split} poly{poly}: rel_l2 {err:.2e}", flush=True)
+        print(f"v6 mode{MODE} B{B} S{S} heads{heads} d{d} split{split} poly{poly}: rel_l2 {err:.2e}", flush=True)
 else:
     shapes = {"c4": (4, 4352, 24, 128), "c2": (1, 1280, 24, 128), "sd3": (8, 4685, 24, 64), "c5": (1, 4608, 24, 128)}
     for rnd in range(2):
@@ -48,7 +49,8 @@ else:
             qkv = torch.randn((B * S, 3 * heads * d), device=DEV, dtype=dt)
             o = torch.empty((B * S, heads * d), device=DEV, dtype=dt)
             line = [f"r{rnd} {name}"]
-            for tag, (sp, po, st) in {"v3": (-1, -1, -1), "v6 poly0": (1, 0, 2), "v6 poly1": (1, 1, 2)}.items():
+            for tag, (sp, po, st) in {"v3": (-1, -1, -1), "v6 p0": (1, 0, 2), "v6 p1": (1, 1, 2), "v6-1T p0": (1, 0, 3),
+                                      "v6-1T p1": (1, 1, 3), "v6-1T p2": (1, 2, 3)}.items():
                 lib.dk_attention_tuning(sp, po, st)
                 t = timeit(lambda: ops.attention(qkv, B, S, heads, d, o))
                 line.append(f"{tag} {4.0 * B * heads * S * S * d / t / 1e12:6.0f} TF/s")
