@@ -611,12 +611,12 @@ extern "C" int dk_attention_fwd(dk_ctx* ctx, int dtype, const void* qkv, int B, 
     return e != nullptr && e[0] == '5';
   }();
   if (use_v5) return dk_launch_attention_v5(ctx, dtype, d, tm, p, stream);
-  static const int env_v6 = [] {   // 6: two threads per row, 7: one thread per row
+  static const int env_v6 = [] {   // 6: two threads per row, 7: one thread per row, 8: 7 + one issuer warp per tile
     const char* e = getenv("DK_ATTENTION_IMPL");
-    return (e != nullptr && (e[0] == '6' || e[0] == '7')) ? e[0] - '0' : 0;
+    return (e != nullptr && (e[0] == '6' || e[0] == '7' || e[0] == '8')) ? e[0] - '0' : 0;
   }();
-  if (env_v6 != 0 || att_tuning(2) == 2 || att_tuning(2) == 3) {   // 64-key steps, double-buffered scores (attention_v6.cu)
-    const int one = (env_v6 == 7 || att_tuning(2) == 3) ? 1 : 0;
+  if (env_v6 != 0 || (att_tuning(2) >= 2 && att_tuning(2) <= 4)) {   // 64-key steps, double-buffered scores (attention_v6.cu)
+    const int one = (env_v6 == 8 || att_tuning(2) == 4) ? 2 : ((env_v6 == 7 || att_tuning(2) == 3) ? 1 : 0);
     CUtensorMap tm64;
     const uint32_t box64[2] = {64, 64};
     if (int rc = dk_make_tmap_16b(ctx, &tm64, qkv, 2, dims, strides, box64)) return rc;

@@ -26,6 +26,9 @@ namespace dk {
 //          maximum exchange, half the mbarrier arrivals; up to 200 registers per thread), 8 TMA, 9 MMA
 constexpr int ATT6_THREADS = 576;
 constexpr int ATT6_THREADS_ONE = 320;
+// ONE = 2: as 1 plus a SECOND MMA issuer warp (warp 10): one issuer per Q tile, so a tile's hand-overs no longer queue
+//          behind the other tile's (ordering is only needed within a tile: PV_w(j) before QK_w(j+2), same thread)
+constexpr int ATT6_THREADS_TWO = 352;
 constexpr int ATT6_BKV = 64;
 
 template <int D>
@@ -47,13 +50,14 @@ struct Att6Cfg {
 };
 
 template <typename T, int D, int POLY4, int ONE>
-__global__ void __launch_bounds__(ONE ? ATT6_THREADS_ONE : ATT6_THREADS, 1)
+__global__ void __launch_bounds__(ONE == 2 ? ATT6_THREADS_TWO : (ONE ? ATT6_THREADS_ONE : ATT6_THREADS), 1)
 attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         const AttParams p) {
   using H16 = Half16<T>;
   using Cfg = Att6Cfg<D>;
   constexpr int KS = Cfg::KS;
   constexpr int W_TMA = ONE ? 8 : 16, W_MMA = ONE ? 9 : 17;
+  constexpr int N_ISS = ONE == 2 ? 2 : 1;   // MMA issuer warps: W_MMA .. W_MMA + N_ISS - 1 (issuer i serves tile i when there are two)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + Cfg::OFF_Q;
@@ -87,9 +91,9 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(q_full, 1);
     for (int i = 0; i < KS; ++i) {
       mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
+      mbar_init(&k_empty[i], N_ISS);   // one commit per issuer
       mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
+      mbar_init(&v_empty[i], N_ISS);
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
@@ -145,8 +149,10 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         par ^= 1;
       }
     }
-  } else if (warp == W_MMA) {
-    // -------------------------------------------------------------------- MMA issuer (converged warp, elected issue)
+  } else if (warp >= W_MMA && warp < W_MMA + N_ISS) {
+    // -------------------------------------------------------------------- MMA issuer(s) (converged warp, elected issue)
+    const int w_lo = N_ISS == 2 ? warp - W_MMA : 0;   // tiles this warp serves: [w_lo, w_hi)
+    const int w_hi = N_ISS == 2 ? warp - W_MMA + 1 : 2;
     constexpr uint32_t idesc_qk = make_idesc_f16(ATT_BQ, ATT6_BKV, H16::is_bf16, false, false);
     constexpr uint32_t idesc_pv = make_idesc_f16(ATT_BQ, D, H16::is_bf16, false, true);
     const uint32_t desc_hi = smem_desc_hi_sw128(1024);
@@ -179,14 +185,13 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 (!first || k != 0) ? 1u : 0u);
       umma_commit(&pv_done[w * 2 + bb]);
     };
-    // prologue: scores of steps 0 and 1 of both tiles
+    // prologue: scores of steps 0 and 1
     mbar_wait(q_full, 0);
     for (int j = 0; j < 2 && j < n_steps; ++j) {
       mbar_wait(&k_full[j], 0);
       tc_fence_after();
       if (elect_one_sync()) {
-        issue_qk(0, j, j);
-        issue_qk(1, j, j);
+        for (int w = w_lo; w < w_hi; ++w) issue_qk(w, j, j);
         umma_commit(&k_empty[j]);
       }
       __syncwarp();
@@ -201,18 +206,17 @@ attention_fwd_v6_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       const int st_k = jn % KS;
       const uint32_t par_k = (jn / KS) & 1;
       mbar_wait(&v_full[st_v], par_v);
-#pragma unroll
-      for (int w = 0; w < 2; ++w) {
+      for (int w = w_lo; w < w_hi; ++w) {
         mbar_wait(&p_full[w * 2 + bb], ph);
-        if (more && w == 0) mbar_wait(&k_full[st_k], par_k);
+        if (more && w == w_lo) mbar_wait(&k_full[st_k], par_k);
         tc_fence_after();
         if (elect_one_sync()) {
           issue_pv(w, st_v, bb, j == 0);
-          if (w == 1) umma_commit(&v_empty[st_v]);
+          if (w == w_hi - 1) umma_commit(&v_empty[st_v]);
           if (j == n_steps - 1) umma_commit(&o_full[w]);
           if (more) {
-            issue_qk(w, st_k, bb);   // buffer bb: PV(j) above is ordered before it on the (in-order) tensor pipe
-            if (w == 1) umma_commit(&k_empty[st_k]);
+            issue_qk(w, st_k, bb);   // buffer bb: PV(j) above is ordered before it (same issuing thread)
+            if (w == w_hi - 1) umma_commit(&k_empty[st_k]);
           }
         }
         __syncwarp();
@@ -472,7 +476,7 @@ static int launch_attention_v6p(dk_ctx* ctx, const CUtensorMap& tmQ, const CUten
     configured = true;
   }
   dim3 grid(dk_ceil_div(p.S, 2 * ATT_BQ), p.heads, p.B);
-  kern<<<grid, ONE ? ATT6_THREADS_ONE : ATT6_THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmKV, p);
+  kern<<<grid, ONE == 2 ? ATT6_THREADS_TWO : (ONE ? ATT6_THREADS_ONE : ATT6_THREADS), Cfg::SMEM_BYTES, stream>>>(tmQ, tmKV, p);
   DK_LAUNCH_CHECK(ctx);
   return 0;
 }
@@ -480,12 +484,16 @@ static int launch_attention_v6p(dk_ctx* ctx, const CUtensorMap& tmQ, const CUten
 }  // namespace dk
 
 // tmQ: the [B*S, 3*heads*d] tensor map with 128-row boxes (dk_attention_fwd builds it); tmKV: the same tensor with
-// 64-row boxes.  poly: exponentials per four on the FMA pipe (0..2).  one_thread_per_row: the 320-thread form.
+// 64-row boxes.  poly: exponentials per four on the FMA pipe (0..2).  one_thread_per_row: 1 = the 320-thread form, 2 = the same with one MMA issuer warp per Q tile.
 int dk_launch_attention_v6(dk_ctx* ctx, int dtype, int d, int poly, int one_thread_per_row, const CUtensorMap& tmQ,
                            const CUtensorMap& tmKV, const dk::AttParams& p, cudaStream_t stream) {
   using namespace dk;
 #define DK_V6(TT, DD)                                                                          \
   do {                                                                                         \
+    if (one_thread_per_row == 2) {                                                             \
+      if (poly <= 0) return launch_attention_v6p<TT, DD, 0, 2>(ctx, tmQ, tmKV, p, stream);     \
+      return launch_attention_v6p<TT, DD, 1, 2>(ctx, tmQ, tmKV, p, stream);                    \
+    }                                                                                          \
     if (one_thread_per_row) {                                                                  \
       if (poly <= 0) return launch_attention_v6p<TT, DD, 0, 1>(ctx, tmQ, tmKV, p, stream);     \
       if (poly == 1) return launch_attention_v6p<TT, DD, 1, 1>(ctx, tmQ, tmKV, p, stream);     \

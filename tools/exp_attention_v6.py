@@ -50,7 +50,7 @@ else:
             o = torch.empty((B * S, heads * d), device=DEV, dtype=dt)
             line = [f"r{rnd} {name}"]
             for tag, (sp, po, st) in {"v3": (-1, -1, -1), "v6 p0": (1, 0, 2), "v6 p1": (1, 1, 2), "v6-1T p0": (1, 0, 3),
-                                      "v6-1T p1": (1, 1, 3), "v6-1T p2": (1, 2, 3)}.items():
+                                      "v6-1T p1": (1, 1, 3), "v6-2I p0": (1, 0, 4), "v6-2I p1": (1, 1, 4)}.items():
                 lib.dk_attention_tuning(sp, po, st)
                 t = timeit(lambda: ops.attention(qkv, B, S, heads, d, o))
                 line.append(f"{tag} {4.0 * B * heads * S * S * d / t / 1e12:6.0f} TF/s")
