@@ -83,6 +83,22 @@ def committed_gemm_traffic():
     return None, None
 
 
+def vae_roofline(decode_ms, images, lat, peaks):
+    """The decode of the last timed step against both roofs (10.472 TFLOP and a 13.46 GB fusion model per
+    1024^2 image, both linear in pixels).  HBM bytes per image are the ncu-measured dram__bytes of one whole decode
+    (profiles/r02_vae_dram_B{1,4}_norm1.txt: 12.44 GB at batch 1, 13.36 GB at batch 4 for 1024^2), not re-measured here."""
+    px = (lat / 128.0) ** 2
+    ms_img = decode_ms / max(images, 1)
+    tflop = 10.472 * px
+    gb = (12.44 if images == 1 else 13.36) * px
+    return {"ms_per_image": ms_img, "tflop_per_image": tflop, "tensor_tflops": tflop / (ms_img * 1e-3),
+            "tensor_frac": tflop / (ms_img * 1e-3) / peaks["bf16_tflops"],
+            "dram_gb_per_image": gb, "dram_gb_model": 13.46 * px, "dram_over_model": gb / (13.46 * px),
+            "dram_gbs": gb / (ms_img * 1e-3), "hbm_frac": gb / (ms_img * 1e-3) / peaks["hbm_gbs"],
+            "dram_source": "profiles/r02_vae_dram_B{1,4}_norm1.txt (ncu dram__bytes_read+write of one decode)",
+            "bound": "tensor (3x3 convs at ~780 FLOP/B); the HBM-bound kernels are listed in DESIGN.md §5"}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -397,6 +413,10 @@ def run_ours(args):
         # the one-time weight replication, split: lazy NCCL communicator creation / rank-0 init / the broadcast itself
         "weights_timing": {k: (round(v, 4) if isinstance(v, float) else v) for k, v in wt.items()},
     }
+    try:
+        line["vae_roofline"] = vae_roofline(split["decode"], per_gpu, lat, peaks)
+    except Exception:  # informational only
+        pass
     if world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline(args.workload)

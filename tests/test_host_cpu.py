@@ -292,3 +292,18 @@ def test_integration_doc_struct_is_current():
         names.append(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*$", first.strip())[0])
         names += [r.strip().lstrip("*").strip() for r in rest]
     assert names == [n for n, _ in _lib.GemmArgs._fields_], (names, [n for n, _ in _lib.GemmArgs._fields_])
+
+
+def test_bench_vae_roofline_helper():
+    """bench.py's VAE roofline object: pure arithmetic on the decode time of the last step"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    peaks = {"bf16_tflops": 1736.7, "bf16_tflops_sustained": 1473.8, "hbm_gbs": 6484.6, "source": "measured"}
+    r = bench.vae_roofline(40.4, 4, 128, peaks)
+    assert abs(r["ms_per_image"] - 10.1) < 1e-9 and abs(r["tensor_frac"] - 10.472 / 10.1e-3 / 1736.7) < 1e-9
+    assert 0.9 < r["dram_over_model"] < 1.0 and 0.15 < r["hbm_frac"] < 0.25
+    r2 = bench.vae_roofline(3.4, 1, 64, peaks)                       # C2: 512^2, a quarter of the pixels
+    assert abs(r2["tflop_per_image"] - 10.472 / 4) < 1e-9 and abs(r2["dram_gb_model"] - 13.46 / 4) < 1e-9

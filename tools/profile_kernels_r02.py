@@ -1,6 +1,8 @@
 """Two launches of every kernel on the C4 / 1024^2-decode path at its real shape, for ONE `ncu --set full` capture
 (tools/ncu_to_json.py keeps the second launch of each kernel):
-  ncu --set full --clock-control none --import-source on -k regex:dk:: -c 80 -o gpurun_out/prof_r02_kernels python tools/profile_kernels_r02.py"""
+  ncu --set full --clock-control none --import-source on -k 'regex:(gemm|attention|conv|groupnorm|softmax_rows|ln_modulate).*_kernel' \
+      -c 80 -o gpurun_out/prof_r02_kernels python tools/profile_kernels_r02.py
+(ncu's -k matches the FUNCTION name without its namespace: `regex:dk::` selects nothing)"""
 import math
 import os
 import sys
