@@ -307,3 +307,19 @@ def test_bench_vae_roofline_helper():
     assert 0.9 < r["dram_over_model"] < 1.0 and 0.15 < r["hbm_frac"] < 0.25
     r2 = bench.vae_roofline(3.4, 1, 64, peaks)                       # C2: 512^2, a quarter of the pixels
     assert abs(r2["tflop_per_image"] - 10.472 / 4) < 1e-9 and abs(r2["dram_gb_model"] - 13.46 / 4) < 1e-9
+
+
+def test_attention_trace_numbers_quoted_in_design():
+    """DESIGN.md §8's clock table is regenerated from the committed timestamp traces (tools/analyze_att_trace.py)"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("att_trace", os.path.join(ROOT, "tools", "analyze_att_trace.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    base = mod.summarize(os.path.join(ROOT, "profiles", "r02_att_trace_call21.txt"))
+    streamed = mod.summarize(os.path.join(ROOT, "profiles", "r02_att_trace_streamed_call22.txt"))
+    assert 3250 <= base["period"] <= 3350 and 3100 <= streamed["period"] <= 3200
+    assert 2080 <= base["tiles"][0]["softmax_total"] <= 2180 and 1860 <= streamed["tiles"][0]["softmax_total"] <= 1960
+    assert 650 <= streamed["tiles"][0]["pv1_qk_issue"] <= 800          # 12 MMAs = 768 tensor clocks, issue is back-pressured
+    design = open(os.path.join(ROOT, "DESIGN.md")).read()
+    assert "**3300 (62 %)**" in design and "**3144 (65 %)**" in design
